@@ -1,0 +1,81 @@
+// Dense allreduce over NVLink peer memory (two-shot, in place, one kernel): every gradient
+// bucket lives in a symmetric IPC allocation, rank r owns the r-th shard, reads that shard from
+// all P buckets with 128-bit peer loads, averages, and stores the result straight into all P
+// buckets.  Cross-GPU synchronisation is per-CTA (CTA i of every rank handles slice i of every
+// shard): a start barrier (everyone's backward has produced the bucket) and an end barrier
+// (everyone's stores have landed) built from st.release.sys / ld.acquire.sys flags.
+//
+// Serves the dense baseline (`compressor none`), the dense warm-up iterations of every sparse
+// scheme and TopkDSA's dense fallback -- reference: dense_allreduce / _dense_allreduce,
+// VGG/allreducer.py:175-180,532-547 (host MPI.Allreduce on NumPy buffers).
+#include "common.cuh"
+#include "oktopk.cuh"
+
+namespace okt {
+
+constexpr int kDenseThreads = 512;
+
+__device__ __forceinline__ void cta_peer_barrier(const DenseParams& p, int phase, uint64_t ticket) {
+    // flag block layout per rank: uint64 [2 phases][gridDim.x][OKT_MAXP]
+    __syncthreads();
+    const int tid = threadIdx.x;
+    if (tid < p.P) {
+        const size_t slot = ((size_t)phase * gridDim.x + blockIdx.x) * OKT_MAXP;
+        fence_acq_rel_sys();
+        st_release_sys_u64(p.flags[tid] + slot + p.rank, ticket);        // tell peer `tid` I am here
+        const uint64_t* mine = p.flags[p.rank] + slot + tid;             // wait for peer `tid`
+        while (ld_acquire_sys_u64(mine) < ticket) { __nanosleep(20); }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kDenseThreads, 1) dense_allreduce_kernel(const DenseParams p) {
+    const int P = p.P, rank = p.rank;
+    // one monotonically increasing ticket per CTA, device resident (CUDA-graph friendly)
+    __shared__ unsigned long long s_ticket;
+    if (threadIdx.x == 0) s_ticket = p.epoch[blockIdx.x] + 1ULL;
+    __syncthreads();
+    const uint64_t ticket = s_ticket;
+
+    cta_peer_barrier(p, 0, ticket);
+
+    const int n4 = p.n >> 2;                      // bucket sizes are padded to a multiple of 4
+    const int shard4 = (n4 + P - 1) / P;
+    const int lo = rank * shard4;
+    const int hi = min(n4, lo + shard4);
+    const float scale = p.scale;
+    for (int v = lo + blockIdx.x * kDenseThreads + threadIdx.x; v < hi; v += gridDim.x * kDenseThreads) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+        for (int s = 0; s < P; ++s) {             // fixed rank order: every rank computes bitwise the same sum
+            const int4 raw = ld_peer_i4(reinterpret_cast<const int4*>(p.bufs[s]) + v);
+            acc.x += __int_as_float(raw.x); acc.y += __int_as_float(raw.y);
+            acc.z += __int_as_float(raw.z); acc.w += __int_as_float(raw.w);
+        }
+        acc.x *= scale; acc.y *= scale; acc.z *= scale; acc.w *= scale;
+#pragma unroll 1
+        for (int t = 0; t < P; ++t) {
+            const int s = (rank + t) % P;
+            st_stream_f4(reinterpret_cast<float4*>(p.bufs[s]) + v, acc);
+        }
+    }
+    // scalar tail (n % 4) is reduced by rank 0's CTA 0
+    if (rank == 0 && blockIdx.x == 0) {
+        for (int i = n4 * 4 + threadIdx.x; i < p.n; i += kDenseThreads) {
+            float a = 0.f;
+            for (int s = 0; s < P; ++s) a += ld_peer_f32(p.bufs[s] + i);
+            a *= scale;
+            for (int s = 0; s < P; ++s) p.bufs[s][i] = a;
+        }
+    }
+    __threadfence_system();
+    cta_peer_barrier(p, 1, ticket);
+    if (threadIdx.x == 0) p.epoch[blockIdx.x] = ticket;
+}
+
+cudaError_t launch_dense_allreduce(const DenseParams& p, int grid, cudaStream_t stream) {
+    dense_allreduce_kernel<<<grid, kDenseThreads, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace okt

@@ -1,0 +1,238 @@
+// Device library shared by the fused kernels: symmetric-block accessors, block scan, grid-wide
+// radix select (exact k-th largest magnitude) and the TMA chunk puller.
+#pragma once
+#include "common.cuh"
+#include "oktopk.cuh"
+
+namespace okt {
+
+// ------------------------------------------------------------------------------------------
+// symmetric-block accessors
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t* rs_mbox(char* b, const SymmLayout& L, int par, int src) {
+    return reinterpret_cast<uint64_t*>(b + L.rs_mbox) + par * OKT_MAXP + src;
+}
+__device__ __forceinline__ float* rs_thr(char* b, const SymmLayout& L, int par, int src) {
+    return reinterpret_cast<float*>(b + L.rs_thr) + par * OKT_MAXP + src;
+}
+__device__ __forceinline__ uint64_t* ag_mbox(char* b, const SymmLayout& L, int par, int src) {
+    return reinterpret_cast<uint64_t*>(b + L.ag_mbox) + par * OKT_MAXP + src;
+}
+__device__ __forceinline__ uint64_t* cut_mbox(char* b, const SymmLayout& L, int par, int src) {
+    return reinterpret_cast<uint64_t*>(b + L.cut_mbox) + par * OKT_MAXP + src;
+}
+__device__ __forceinline__ int* cut_data(char* b, const SymmLayout& L, int par, int src) {
+    return reinterpret_cast<int*>(b + L.cut_data) + (par * OKT_MAXP + src) * OKT_MAXP;
+}
+__device__ __forceinline__ int* send_idx(char* b, const SymmLayout& L, int P, int par, int dst) {
+    return reinterpret_cast<int*>(b + L.send_idx) + ((size_t)par * P + dst) * L.cap;
+}
+__device__ __forceinline__ float* send_val(char* b, const SymmLayout& L, int P, int par, int dst) {
+    return reinterpret_cast<float*>(b + L.send_val) + ((size_t)par * P + dst) * L.cap;
+}
+__device__ __forceinline__ int* gat_idx(char* b, const SymmLayout& L, int par) {
+    return reinterpret_cast<int*>(b + L.gat_idx) + (size_t)par * L.gcap;
+}
+__device__ __forceinline__ float* gat_val(char* b, const SymmLayout& L, int par) {
+    return reinterpret_cast<float*>(b + L.gat_val) + (size_t)par * L.gcap;
+}
+
+// ------------------------------------------------------------------------------------------
+// block-wide exclusive scan of one int per thread (kThreads threads); returns exclusive prefix,
+// *total gets the block sum.  s_w: kWarps + 1 ints of shared scratch.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int block_excl_scan(int v, int* s_w, int* total) {
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    __syncthreads();
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = (lane < kWarps) ? s_w[lane] : 0;
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        if (lane < kWarps) s_w[lane] = winc - w;
+        if (lane == kWarps - 1) s_w[kWarps] = winc;
+    }
+    __syncthreads();
+    *total = s_w[kWarps];
+    return s_w[warp] + inc - v;
+}
+
+// ------------------------------------------------------------------------------------------
+// Exact k-th largest magnitude over a set of segments: 3-pass radix select (11+10+10 bits of the
+// magnitude bit pattern), grid-wide.  The per-pass digit histogram is built in shared memory,
+// merged into st->hist, and block 0 picks the digit; state travels in st->sel_prefix/sel_krem.
+// ------------------------------------------------------------------------------------------
+struct Seg { const float* ptr; int count; };
+
+__device__ __forceinline__ void digit_of_pass(int pass, int& shift, int& nbits) {
+    shift = (pass == 0) ? 20 : (pass == 1 ? 10 : 0);
+    nbits = (pass == 0) ? 11 : 10;
+}
+
+static __device__ void radix_pick_digit(OktState* st, int pass, uint32_t k_in, int* s_w) {
+    // block 0 only; all kThreads threads
+    int shift, nbits;
+    digit_of_pass(pass, shift, nbits);
+    const int bins = 1 << nbits;
+    const int per = (bins + kThreads - 1) / kThreads;
+    uint32_t prefix = (pass == 0) ? 0u : st->sel_prefix;
+    uint32_t krem = (pass == 0) ? k_in : st->sel_krem;
+    // thread t owns reversed bins [t*per, (t+1)*per)  (reversed: rb = bins-1-b, so ascending rb = descending magnitude)
+    int mysum = 0;
+    for (int j = 0; j < per; ++j) {
+        int rb = threadIdx.x * per + j;
+        if (rb < bins) mysum += (int)st->hist[bins - 1 - rb];
+    }
+    int total;
+    int excl = block_excl_scan(mysum, s_w, &total);
+    if (krem > (uint32_t)total) krem = (uint32_t)total;       // fewer candidates than k: take the smallest
+    __shared__ uint32_t s_pick[2];
+    if (threadIdx.x == 0) { s_pick[0] = 0; s_pick[1] = 0; }
+    __syncthreads();
+    if (total > 0) {
+        int run = excl;
+        for (int j = 0; j < per; ++j) {
+            int rb = threadIdx.x * per + j;
+            if (rb < bins) {
+                int c = (int)st->hist[bins - 1 - rb];
+                if ((uint32_t)run < krem && krem <= (uint32_t)(run + c)) {
+                    s_pick[0] = (uint32_t)(bins - 1 - rb);
+                    s_pick[1] = krem - (uint32_t)run;
+                }
+                run += c;
+            }
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < kHistBins; b += kThreads) st->hist[b] = 0;
+    if (threadIdx.x == 0) {
+        st->sel_prefix = (prefix << nbits) | s_pick[0];
+        st->sel_krem = s_pick[1];
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void hist_add(uint32_t* s_hist, float v, int pass, uint32_t prefix) {
+    uint32_t key = abs_bits(v);
+    int shift, nbits;
+    digit_of_pass(pass, shift, nbits);
+    if (pass == 0 || (key >> (shift + nbits)) == prefix)
+        atomicAdd(&s_hist[(key >> shift) & ((1u << nbits) - 1u)], 1u);
+}
+
+__device__ __forceinline__ void hist_flush(OktState* st, uint32_t* s_hist) {
+    __syncthreads();
+    for (int b = threadIdx.x; b < kHistBins; b += kThreads) {
+        uint32_t c = s_hist[b];
+        if (c) atomicAdd(&st->hist[b], c);
+        s_hist[b] = 0;
+    }
+    __syncthreads();
+}
+
+// returns the bit pattern of the k-th largest |v| (0 if there are no candidates)
+static __device__ float grid_kth_abs(const Seg* segs, int nseg, bool remote, uint32_t k, OktState* st,
+                              uint32_t* s_hist, int* s_w, int first_pass) {
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gthreads = gridDim.x * blockDim.x;
+    for (int pass = 0; pass < 3; ++pass) {
+        if (pass >= first_pass) {
+            uint32_t prefix = (pass == 0) ? 0u : st->sel_prefix;
+            for (int s = 0; s < nseg; ++s) {
+                const float* ptr = segs[s].ptr;
+                const int cnt = segs[s].count;
+                for (int i = gtid; i < cnt; i += gthreads) {
+                    float v = remote ? ld_peer_f32(ptr + i) : __ldcg(ptr + i);
+                    hist_add(s_hist, v, pass, prefix);
+                }
+            }
+            hist_flush(st, s_hist);
+        }
+        grid_sync(&st->bar);
+        if (blockIdx.x == 0) radix_pick_digit(st, pass, k, s_w);
+        grid_sync(&st->bar);
+    }
+    return __uint_as_float(st->sel_prefix);
+}
+
+// ------------------------------------------------------------------------------------------
+// chunk puller: double-buffered TMA bulk copies of (idx,val) chunks from (possibly remote) slots
+// ------------------------------------------------------------------------------------------
+struct PullSmem {
+    int idx[2][kChunk];
+    float val[2][kChunk];
+    uint64_t bar[2];
+};
+
+struct ChunkSrc { const int* idx; const float* val; int count; };
+
+// Calls fn(src_index, entry_idx, entry_val) for every valid entry of the chunks this CTA owns.
+// The chunk list is the concatenation over sources (in the order given) of ceil(count/kChunk) chunks,
+// dealt round-robin to CTAs.  pipe_it carries the mbarrier phase across calls.
+template <class F>
+__device__ __forceinline__ void pull_chunks(const ChunkSrc* srcs, int nsrc, bool use_tma, PullSmem* sm,
+                                            uint32_t& pipe_it, F&& fn) {
+    int total = 0;
+    for (int s = 0; s < nsrc; ++s) total += (srcs[s].count + kChunk - 1) / kChunk;
+    const int G = gridDim.x, c0 = blockIdx.x;
+    const int nmine = (total > c0) ? (total - c0 + G - 1) / G : 0;
+    if (nmine == 0) return;
+
+    auto locate = [&](int cid, int& s, int& off) {
+        int acc = 0;
+        for (s = 0; s < nsrc; ++s) {
+            int nc = (srcs[s].count + kChunk - 1) / kChunk;
+            if (cid < acc + nc) { off = (cid - acc) * kChunk; return; }
+            acc += nc;
+        }
+        s = nsrc - 1; off = 0;
+    };
+
+    if (use_tma) {
+        auto issue = [&](int j) {
+            int s, off;
+            locate(c0 + j * G, s, off);
+            uint32_t it = pipe_it + j;
+            int stg = it & 1;
+            fence_proxy_async_smem();
+            mbar_expect_tx(&sm->bar[stg], 2u * kChunk * 4u);
+            tma_load_1d(sm->idx[stg], srcs[s].idx + off, kChunk * 4u, &sm->bar[stg]);
+            tma_load_1d(sm->val[stg], srcs[s].val + off, kChunk * 4u, &sm->bar[stg]);
+        };
+        if (threadIdx.x == 0) issue(0);
+        for (int j = 0; j < nmine; ++j) {
+            if (threadIdx.x == 0 && j + 1 < nmine) issue(j + 1);
+            uint32_t it = pipe_it + j;
+            int stg = it & 1;
+            mbar_wait(&sm->bar[stg], (it >> 1) & 1u);
+            int s, off;
+            locate(c0 + j * G, s, off);
+            const int valid = min(kChunk, srcs[s].count - off);
+            for (int e = threadIdx.x; e < valid; e += kThreads) fn(s, sm->idx[stg][e], sm->val[stg][e]);
+            __syncthreads();
+        }
+        pipe_it += nmine;
+    } else {
+        for (int j = 0; j < nmine; ++j) {
+            int s, off;
+            locate(c0 + j * G, s, off);
+            const int valid = min(kChunk, srcs[s].count - off);
+            for (int e = threadIdx.x; e < valid; e += kThreads)
+                fn(s, ld_peer_s32(srcs[s].idx + off + e), ld_peer_f32(srcs[s].val + off + e));
+        }
+    }
+}
+
+
+}  // namespace okt

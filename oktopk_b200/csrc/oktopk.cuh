@@ -1,0 +1,161 @@
+// Shared declarations of the fused sparse-allreduce kernels: device-resident per-bucket state,
+// launch parameters, symmetric-block layout.  Included by the .cu files (nvcc) and bindings.cpp (g++).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#ifndef OKT_MAXP
+#define OKT_MAXP 16
+#endif
+
+namespace okt {
+
+constexpr int kThreads = 512;             // threads per CTA of the persistent kernels
+constexpr int kWarps = kThreads / 32;
+constexpr int kChunk = 1024;              // (idx,val) entries per pulled chunk (4 KB + 4 KB)
+constexpr int kHistBins = 2048;           // 11-bit radix digit
+constexpr int kMaxWarpsTotal = 16384;     // per-warp counters for the quantile cuts
+constexpr int kGuardMax = 8;
+
+// ---- device-resident, zero-initialised, one per bucket ---------------------------------------
+struct OktState {
+    unsigned long long bar;               // grid-barrier ticket counter
+    float local_thr;                      // threshold carried into the next call (after adaptation)
+    float local_thr_used;                 // threshold actually applied in the last call (after guard)
+    float global_thr;
+    uint32_t epoch;                       // completed calls; the running call uses epoch + 1
+    int edges[OKT_MAXP + 1];              // region edges, edges[0] = 0, edges[P] = n
+    int send_cursor[OKT_MAXP];            // per-destination slot cursors (reset in-kernel)
+    int gather_cursor;
+    int guard_counts[kGuardMax];          // #(|acc| > thr0 * f^j)
+    uint32_t sel_prefix;                  // radix-select running prefix / remaining rank
+    uint32_t sel_krem;
+    int cuts[OKT_MAXP];
+    // statistics of the last call (read lazily by the host; never on the hot path)
+    int stat_local_count;
+    int stat_global_count;
+    int stat_recv_total;                  // entries pulled in the reduce phase
+    int stat_gather_total;                // entries pulled in the final phase
+    int stat_overflow_send;               // cumulative drops because a slot was full
+    int stat_overflow_gather;
+    int stat_mode;
+    int pad0;
+    double gs_sum, gs_sumsq;              // Gaussiank moments
+    uint32_t hist[kHistBins];
+    int wcounts[kMaxWarpsTotal];
+};
+
+// ---- byte offsets inside every rank's symmetric block (identical on all ranks) -----------------
+struct SymmLayout {
+    size_t rs_mbox;      // uint64 [2][MAXP]       reduce-scatter mailbox: (epoch<<32 | count) from src
+    size_t rs_thr;       // float  [2][MAXP]       src's final local threshold (receiver-side filter)
+    size_t ag_mbox;      // uint64 [2][MAXP]       allgather mailbox
+    size_t cut_mbox;     // uint64 [2][MAXP]
+    size_t cut_data;     // int32  [2][MAXP][MAXP]
+    size_t send_idx;     // int32  [2][P][cap]     my selections, bucketed by destination region
+    size_t send_val;     // float  [2][P][cap]
+    size_t gat_idx;      // int32  [2][gcap]       my region's globally selected entries
+    size_t gat_val;      // float  [2][gcap]
+    size_t total;
+    int cap, gcap;
+};
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+inline SymmLayout make_layout(int P, int cap, int gcap) {
+    SymmLayout L;
+    size_t o = 0;
+    L.rs_mbox = o;  o += sizeof(uint64_t) * 2 * OKT_MAXP;
+    L.rs_thr = o;   o += sizeof(float) * 2 * OKT_MAXP;
+    L.ag_mbox = o;  o += sizeof(uint64_t) * 2 * OKT_MAXP;
+    L.cut_mbox = o; o += sizeof(uint64_t) * 2 * OKT_MAXP;
+    L.cut_data = o; o += sizeof(int) * 2 * OKT_MAXP * OKT_MAXP;
+    o = align_up(o, 1024);
+    L.send_idx = o; o += sizeof(int) * 2 * (size_t)P * cap;   o = align_up(o, 1024);
+    L.send_val = o; o += sizeof(float) * 2 * (size_t)P * cap; o = align_up(o, 1024);
+    L.gat_idx = o;  o += sizeof(int) * 2 * (size_t)gcap;      o = align_up(o, 1024);
+    L.gat_val = o;  o += sizeof(float) * 2 * (size_t)gcap;    o = align_up(o, 1024);
+    L.total = o;
+    L.cap = cap;
+    L.gcap = gcap;
+    return L;
+}
+
+enum Phase : int {
+    PH_LOCAL = 0,      // two-pass iterations: acc -> residual, exact k-th |acc| or guard, re-partition
+    PH_PACK = 1,       // (accumulate +) select + pack per destination region
+    PH_PUBLISH_RS = 2, // finalise threshold, publish counts to the region owners
+    PH_REDUCE = 3,     // pull every source's slot for my region, scatter-add
+    PH_GSELECT = 4,    // global selection on my region, pack the allgather slot
+    PH_PUBLISH_AG = 5,
+    PH_FINAL = 6,      // pull all slots, (exact top-k,) scatter result, clear residual, adapt
+    PH_END = 7
+};
+
+enum ResidualMode : int { RES_OKTOPK = 0, RES_LOCAL_GT = 1, RES_LOCAL_GE = 2 };
+enum GlobalMode : int { GLB_THRESHOLD = 0, GLB_EXACT_TOPK = 1, GLB_ALL_NONZERO = 2 };
+
+struct OktParams {
+    float* g;            // gradient bucket (result written in place)
+    float* res;          // residual / accumulator
+    OktState* st;
+    char* peers[OKT_MAXP];   // every rank's symmetric block as mapped into this process
+    SymmLayout L;
+    int n, P, rank, k;
+    int exact_local, repartition, uniform_regions;
+    int residual_mode, global_mode;
+    int deterministic, pull_tma;
+    int phase_begin, phase_end;
+    int guard_loops, guard_limit;
+    float guard_factor;
+    double l_low_cnt, l_high_cnt;       // local adaptation bounds, already multiplied by k
+    float l_factor;
+    double g_low_cnt, g_high_cnt;
+    float g_inc, g_dec;
+};
+
+// ---- gather-type schemes (TopkAopt / Gaussiank / TopkA): select -> own slot -> everyone adds all ---
+enum GatherSelect : int { GS_THRESHOLD_REUSE = 0, GS_GAUSSIAN = 1, GS_EXACT_TOPK = 2 };
+
+struct GatherParams {
+    float* g;
+    float* res;
+    OktState* st;
+    char* peers[OKT_MAXP];
+    SymmLayout L;
+    int n, P, rank, k;
+    int select_mode;          // GatherSelect
+    int exact_now;            // GS_THRESHOLD_REUSE: recompute the exact threshold in this call
+    int gauss_mode;           // 0 vgg, 1 lstm, 2 bert
+    int gauss_loops;
+    float gauss_factor;
+    float density;
+    int pull_tma;
+};
+
+// ---- dense allreduce over peer memory -------------------------------------------------------------
+struct DenseParams {
+    float* bufs[OKT_MAXP];    // every rank's gradient bucket (symmetric allocation)
+    uint64_t* flags[OKT_MAXP];  // every rank's flag block: uint64 [2][grid][MAXP]
+    unsigned long long* epoch;  // local, one counter per CTA
+    int n, P, rank;
+    float scale;              // 1/P
+};
+
+// ---- host-callable launchers (implemented in the .cu files) ----------------------------------------
+int okt_max_coop_grid(int device);
+cudaError_t launch_oktopk(const OktParams& p, int grid, cudaStream_t stream);
+cudaError_t launch_gather_scheme(const GatherParams& p, int grid, cudaStream_t stream);
+cudaError_t launch_dense_allreduce(const DenseParams& p, int grid, cudaStream_t stream);
+cudaError_t launch_kth_abs(const float* x, int n, int k, OktState* st, float* out_thr, int grid, cudaStream_t stream);
+cudaError_t launch_fused_sgd(float* p, float* g, float* mom, int n, float lr, float momentum, float dampening,
+                             float weight_decay, int nesterov, int first_step, int zero_grad, float grad_scale,
+                             cudaStream_t stream);
+cudaError_t launch_fused_bert_adam(float* p, float* g, float* m, float* v, int n, float lr, float b1, float b2,
+                                   float eps, float weight_decay, int zero_grad, cudaStream_t stream);
+cudaError_t launch_momentum_correct(float* g, float* buf, int n, float momentum, cudaStream_t stream);
+cudaError_t launch_l2norm_sq(const float* x, int n, float* out, cudaStream_t stream);
+cudaError_t launch_scale(float* x, int n, const float* norm_sq, float max_norm, cudaStream_t stream);
+
+}  // namespace okt

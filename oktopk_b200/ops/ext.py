@@ -1,0 +1,59 @@
+"""Loader of the native extension.  On a GPU box a missing/unloadable extension is a hard error
+(no silent eager fallback: the CUDA path is the product); on a CPU-only box ``available()`` is
+simply False and the torch.distributed ("dist") backend is used."""
+from __future__ import annotations
+
+import importlib
+import os
+from typing import Optional
+
+_C = None
+_ERR: Optional[BaseException] = None
+
+
+def load(build_if_missing: bool = True):
+    """Import ``oktopk_b200._C`` (building it in-tree first if nvcc is around and it is stale)."""
+    global _C, _ERR
+    if _C is not None:
+        return _C
+    try:
+        from . import build as _b
+        if build_if_missing and _b.needs_build() and os.environ.get("OKTOPK_NO_BUILD", "0") != "1":
+            _b.build()
+        _C = importlib.import_module("oktopk_b200._C")
+        _ERR = None
+    except BaseException as e:  # noqa: BLE001
+        _ERR = e
+        _C = None
+    return _C
+
+
+def available() -> bool:
+    return load() is not None
+
+
+def require():
+    c = load()
+    if c is None:
+        raise RuntimeError("oktopk_b200 native extension (_C) is not available: %r" % (_ERR,))
+    return c
+
+
+class DevPtr:
+    """A raw device allocation exposed through ``__cuda_array_interface__`` so that
+    ``torch.as_tensor(DevPtr(...), device='cuda')`` aliases it without a copy."""
+
+    def __init__(self, ptr: int, numel: int, typestr: str = "<f4"):
+        self.ptr, self.numel, self.typestr = int(ptr), int(numel), typestr
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": (self.numel,), "typestr": self.typestr, "data": (self.ptr, False), "version": 3,
+                "strides": None}
+
+
+def tensor_from_ptr(ptr: int, numel: int, dtype="float32", device=None):
+    import torch
+    ts = {"float32": "<f4", "int32": "<i4", "uint8": "|u1", "int64": "<i8"}[dtype]
+    dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    return torch.as_tensor(DevPtr(ptr, numel, ts), device=dev)

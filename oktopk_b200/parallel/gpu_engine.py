@@ -1,0 +1,214 @@
+"""The B200 engine: one ``CudaBucketEngine`` per gradient bucket drives the fused sm_100a kernels.
+
+Host-side role is *scheduling only*: it knows the iteration counter (which iterations recompute
+exact thresholds / re-partition regions) and enqueues ONE persistent cooperative
+kernel per bucket per step on the communication stream.  Thresholds, region edges, slot cursors,
+flag epochs and statistics are device resident; there is no host synchronisation, no NCCL call
+and no count handshake on the host (the reference needs >= 3P+6 staging copies and 4-6 blocking
+MPI calls per step, SURVEY 3.3 notes).
+
+Memory per bucket (one IPC allocation, mapped by every peer):
+    [ flat fp32 gradient bucket | mailboxes + send slots + gather slots | dense-allreduce flags ]
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from ..config import OkTopkConfig
+from ..ops import ext
+from .state import SparseState, uniform_boundaries, offsets_of
+from .symm import SymmBlock
+from .world import World
+
+RES_OKTOPK, RES_LOCAL_GT, RES_LOCAL_GE = 0, 1, 2
+GLB_THRESHOLD, GLB_EXACT_TOPK, GLB_ALL_NONZERO = 0, 1, 2
+GS_THRESHOLD_REUSE, GS_GAUSSIAN, GS_EXACT_TOPK = 0, 1, 2
+
+_FUSED = {"oktopk", "topkSA", "topkDSA", "gaussiankSA"}
+_GATHER = {"topkA", "topkAopt", "gaussiank", "gaussiankconcat"}
+_DIST_ONLY = {"topkA2", "gtopk"}        # tree / re-selection schemes run on NCCL + torch ops
+
+
+def _round_up(x: int, m: int) -> int:
+    return (int(x) + m - 1) // m * m
+
+
+class CudaBucketEngine:
+    def __init__(self, numel: int, cfg: OkTopkConfig, world: World, name: str = "bucket",
+                 max_density: Optional[float] = None, dense_grid: int = 64):
+        self.C = ext.require()
+        C = self.C
+        self.cfg = cfg
+        self.world = world
+        self.name = name
+        self.P = world.size
+        self.rank = world.rank
+        if self.P > C.MAXP:
+            raise ValueError("world size %d exceeds OKT_MAXP=%d" % (self.P, C.MAXP))
+        self.n = int(numel)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        dmax = max_density if max_density is not None else cfg.density
+        if cfg.dynamic_densities:
+            dmax = max(dmax, max(cfg.dynamic_densities))
+        kmax = max(int(self.n * dmax), 1)
+        chunk = C.CHUNK
+        self.cap = _round_up(max(cfg.slot_factor * kmax / self.P, chunk), chunk) + chunk
+        self.gcap = _round_up(max(cfg.gather_factor * kmax / self.P, 2 * kmax, chunk), chunk) + chunk
+        info = C.layout_info(self.P, self.cap, self.gcap)
+        self.layout = info
+        self.grid = C.max_coop_grid(self.device.index)
+        if cfg.comm_ctas > 0:
+            self.grid = min(self.grid, cfg.comm_ctas)
+        self.dense_grid = dense_grid
+        # ---- one symmetric allocation: [grad | comm block | dense flags] -------------------
+        self.grad_bytes = _round_up(self.n * 4, 4096)
+        self.comm_off = self.grad_bytes
+        self.flags_off = self.comm_off + _round_up(info["total"], 4096)
+        flags_bytes = 8 * 2 * self.dense_grid * C.MAXP
+        self.block = SymmBlock(self.flags_off + _round_up(flags_bytes, 4096), world)
+        self.grad = self.block.tensor(0, self.n, "float32")
+        self.peer_comm = [p + self.comm_off for p in self.block.ptrs]
+        self.peer_grad = [p for p in self.block.ptrs]
+        self.peer_flags = [p + self.flags_off for p in self.block.ptrs]
+        # ---- local device state -------------------------------------------------------------
+        self.state_ptr = C.dev_alloc_zero(C.state_bytes())
+        self.dense_epoch_ptr = C.dev_alloc_zero(8 * self.dense_grid)
+        self.residual = torch.zeros(self.n, dtype=torch.float32, device=self.device)
+        self.host = SparseState(self.n, self.P)          # counter + (lazily refreshed) mirrors
+        self._write_edges(self.host.region_offsets + [self.n])
+        self._dist_state: Optional[SparseState] = None
+        self.last_mode = ""
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self, stream: Optional[torch.cuda.Stream]) -> int:
+        return (stream or torch.cuda.current_stream()).cuda_stream
+
+    def _write_edges(self, edges: List[int], local_thr: float = 0.0, global_thr: float = 0.0) -> None:
+        self.C.write_state(self.state_ptr, float(local_thr), float(global_thr), [int(e) for e in edges],
+                           torch.cuda.current_stream().cuda_stream)
+
+    def k_now(self, density: Optional[float] = None) -> int:
+        d = self.cfg.density if density is None else density
+        return max(int(self.n * d), 1)
+
+    # ------------------------------------------------------------------ the step
+    def reduce(self, compressor: str, density: Optional[float] = None,
+               stream: Optional[torch.cuda.Stream] = None, g: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Allreduce this bucket in place (``self.grad`` unless an external ``g`` is given)."""
+        cfg = self.cfg
+        st = self.host
+        ext_g = g is not None and g.data_ptr() != self.grad.data_ptr()
+        dense = (not cfg.sparse) or compressor in ("none", None) or st.counter < cfg.warmup_iters
+        s = self._stream(stream)
+        if dense:
+            if ext_g:
+                self.grad.copy_(g)
+            self._dense(s)
+            if ext_g:
+                g.copy_(self.grad)
+            self.last_mode = "dense"
+        elif compressor in _FUSED:
+            self._fused(compressor, density, s, g if ext_g else self.grad)
+        elif compressor in _GATHER:
+            self._gather(compressor, density, s, g if ext_g else self.grad)
+        elif compressor in _DIST_ONLY:
+            self._dist(compressor, density, g if ext_g else self.grad)
+        else:
+            raise KeyError("unknown compressor %r" % (compressor,))
+        st.counter += 1
+        return g if ext_g else self.grad
+
+    def _dense(self, s: int) -> None:
+        if self.P == 1:
+            return
+        self.C.dense_run(self.peer_grad, self.peer_flags, self.dense_epoch_ptr, self.n, self.rank,
+                         self.dense_grid, s)
+
+    def _fused(self, compressor: str, density: Optional[float], s: int, g: torch.Tensor) -> None:
+        cfg = self.cfg
+        k = self.k_now(density)
+        it = self.host.counter - cfg.warmup_iters
+        o: Dict = {"pull_tma": 1 if cfg.pull_mode == "tma" else 0, "deterministic": int(cfg.deterministic),
+                   "split_phases": 0 if cfg.fused else 1}
+        if compressor == "oktopk":
+            o.update(
+                exact_local=int(it % cfg.local_recompute_interval == 0),
+                repartition=int(it % cfg.repartition_interval == 0 and self.P > 1),
+                residual_mode=RES_OKTOPK,
+                global_mode=GLB_EXACT_TOPK if it % cfg.global_recompute_interval == 0 else GLB_THRESHOLD,
+                guard_loops=cfg.overselect_guard_loops,
+                guard_limit=cfg.overselect_guard_num * k // cfg.overselect_guard_den,
+                guard_factor=cfg.overselect_guard_factor,
+                l_low_cnt=cfg.local_adapt_low * k, l_high_cnt=cfg.local_adapt_high * k, l_factor=cfg.local_adapt_factor,
+                g_low_cnt=cfg.global_adapt_low * k, g_high_cnt=cfg.global_adapt_high * k,
+                g_inc=cfg.global_adapt_inc, g_dec=cfg.global_adapt_dec,
+            )
+        else:  # TopkDSA / gaussiankSA: exact threshold every call, uniform regions, all non-zeros gathered
+            o.update(exact_local=1, repartition=0,
+                     residual_mode=RES_LOCAL_GT if compressor == "gaussiankSA" else RES_LOCAL_GE,
+                     global_mode=GLB_ALL_NONZERO, guard_loops=0, guard_limit=0)
+        self.C.oktopk_run(g.data_ptr(), self.residual.data_ptr(), self.state_ptr, self.peer_comm, self.n,
+                          self.rank, k, self.cap, self.gcap, o, self.grid, s)
+        self.last_mode = compressor
+
+    def _gather(self, compressor: str, density: Optional[float], s: int, g: torch.Tensor) -> None:
+        cfg = self.cfg
+        d = cfg.density if density is None else density
+        k = self.k_now(density)
+        it = self.host.counter - cfg.warmup_iters
+        o: Dict = {"density": d, "pull_tma": 1 if cfg.pull_mode == "tma" else 0}
+        if compressor == "topkA":
+            o["select_mode"] = GS_EXACT_TOPK
+        elif compressor == "topkAopt":
+            o["select_mode"] = GS_THRESHOLD_REUSE
+            o["exact_now"] = int(it % cfg.topkaopt_recompute_interval == 0)
+        else:
+            o["select_mode"] = GS_GAUSSIAN
+            o["gauss_mode"] = {"vgg": 0, "lstm": 1, "bert": 2}[cfg.gaussian_mode]
+            o["gauss_loops"] = cfg.gaussian_loops
+            o["gauss_factor"] = cfg.gaussian_factor
+        self.C.gather_run(g.data_ptr(), self.residual.data_ptr(), self.state_ptr, self.peer_comm, self.n,
+                          self.rank, k, self.cap, self.gcap, o, self.grid, s)
+        self.last_mode = compressor
+
+    def _dist(self, compressor: str, density: Optional[float], g: torch.Tensor) -> None:
+        from .algorithms import ALGORITHMS
+        if self._dist_state is None:
+            self._dist_state = SparseState(self.n, self.P)
+            self._dist_state.residual = self.residual
+        self._dist_state.counter = self.host.counter
+        ALGORITHMS[compressor](g, self._dist_state, self.cfg, self.world, density)
+        self.last_mode = compressor
+
+    # ------------------------------------------------------------------ observability / checkpoint
+    def stats(self) -> Dict:
+        """Synchronous read of the device-resident state (never called on the hot path)."""
+        d = self.C.read_state(self.state_ptr, self.P, torch.cuda.current_stream().cuda_stream)
+        d["counter"] = self.host.counter
+        d["mode"] = self.last_mode
+        d["cap"], d["gcap"], d["grid"] = self.cap, self.gcap, self.grid
+        # scalars moved by this rank in the last call (idx + val per entry), cf. the 6k(P-1)/P bound
+        d["volume_elems"] = 2 * (d["recv_total"] + d["gather_total"])
+        return d
+
+    def state_dict(self) -> Dict:
+        d = self.stats()
+        return {"numel": self.n, "world": self.P, "counter": self.host.counter, "local_thr": d["local_thr"],
+                "global_thr": d["global_thr"], "boundaries": [d["edges"][i + 1] - d["edges"][i] for i in range(self.P)],
+                "region_offsets": d["edges"][:-1], "residual": self.residual.detach().cpu().clone()}
+
+    def load_state_dict(self, sd: Dict) -> None:
+        assert sd["numel"] == self.n
+        self.host.counter = int(sd["counter"])
+        if sd.get("residual") is not None:
+            self.residual.copy_(sd["residual"].to(self.device))
+        if sd["world"] == self.P:
+            edges = list(sd["region_offsets"]) + [self.n]
+        else:
+            edges = offsets_of(uniform_boundaries(self.n, self.P)) + [self.n]
+        self._write_edges(edges, sd["local_thr"], sd["global_thr"])
+
+    def close(self) -> None:
+        self.block.close()
