@@ -20,9 +20,12 @@ __version__ = "0.1.0"
 
 def __getattr__(name):
     # heavier modules are imported lazily so that `import oktopk_b200` stays cheap
-    if name in ("DistributedOptimizer", "BertAdam"):
+    if name in ("DistributedOptimizer", "BertAdam", "broadcast_parameters"):
         from . import optimizer as _o
         return getattr(_o, name)
+    if name in ("optimizer", "models", "train", "utils", "ops", "parallel", "compression", "config"):
+        import importlib
+        return importlib.import_module("." + name, __name__)
     if name == "AllReducer":
         from .parallel.allreducer import AllReducer
         return AllReducer

@@ -10,6 +10,33 @@ from typing import Optional
 _C = None
 _ERR: Optional[BaseException] = None
 
+# kernels launched by this package since import (the bench reports the delta over its timed region)
+LAUNCH_COUNT = {"total": 0}
+_LAUNCHERS = {"oktopk_run": 1, "gather_run": 1, "dense_run": 1, "kth_abs": 1, "fused_sgd": 1, "fused_bert_adam": 1,
+              "momentum_correct": 1, "clip_by_norm": 2}
+
+
+class _CountingModule:
+    """Thin proxy over the native module that counts kernel launches per entry point."""
+
+    def __init__(self, mod):
+        self._mod = mod
+        for name, per_call in _LAUNCHERS.items():
+            setattr(self, name, self._wrap(getattr(mod, name), name, per_call))
+
+    def _wrap(self, fn, name, per_call):
+        def call(*a, **kw):
+            n = per_call
+            if name == "oktopk_run" and isinstance(a[9], dict) and a[9].get("split_phases"):
+                n = 7
+            LAUNCH_COUNT["total"] += n
+            LAUNCH_COUNT[name] = LAUNCH_COUNT.get(name, 0) + n
+            return fn(*a, **kw)
+        return call
+
+    def __getattr__(self, name):
+        return getattr(self._mod, name)
+
 
 def load(build_if_missing: bool = True):
     """Import ``oktopk_b200._C`` (building it in-tree first if nvcc is around and it is stale)."""
@@ -20,7 +47,7 @@ def load(build_if_missing: bool = True):
         from . import build as _b
         if build_if_missing and _b.needs_build() and os.environ.get("OKTOPK_NO_BUILD", "0") != "1":
             _b.build()
-        _C = importlib.import_module("oktopk_b200._C")
+        _C = _CountingModule(importlib.import_module("oktopk_b200._C"))
         _ERR = None
     except BaseException as e:  # noqa: BLE001
         _ERR = e

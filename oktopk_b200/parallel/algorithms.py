@@ -231,6 +231,7 @@ def topka_allreduce(g, st: SparseState, cfg: OkTopkConfig, world: World, density
             lost = ~keep[idx]
             res[idx[lost]] += vals[lost]
         g.div_(P)
+        st.local_thr = float(vals.abs().min())
         st.last_local_count = k
         st.last_global_count = int((g != 0).sum())
         st.last_volume_elems = 4 * k * (P - 1)

@@ -23,6 +23,18 @@ from .state import SparseState, offsets_of, uniform_boundaries
 
 
 # --------------------------------------------------------------------------- helpers
+import numpy as _np
+
+
+def f32_mul(a: float, b: float) -> float:
+    """Thresholds live in fp32 on the device: mirror the kernel's arithmetic exactly."""
+    return float(_np.float32(a) * _np.float32(b))
+
+
+def f32_div(a: float, b: float) -> float:
+    return float(_np.float32(a) / _np.float32(b))
+
+
 def kth_largest_abs(x: torch.Tensor, k: int) -> float:
     k = max(min(k, x.numel()), 1)
     return float(torch.topk(x.abs().view(-1), k=k).values[-1])
@@ -35,7 +47,7 @@ def guard_threshold(absx: torch.Tensor, thr: float, k: int, cfg: OkTopkConfig) -
     limit = cfg.overselect_guard_num * k // cfg.overselect_guard_den
     for _ in range(cfg.overselect_guard_loops):
         if int((absx > thr).sum()) > limit:
-            thr *= cfg.overselect_guard_factor
+            thr = f32_mul(thr, cfg.overselect_guard_factor)
         else:
             break
     return thr
@@ -64,17 +76,17 @@ def boundaries_from_cuts(avg_cuts: Sequence[int], n: int) -> Tuple[List[int], Li
 
 def adapt_local(thr: float, count: int, k: int, cfg: OkTopkConfig) -> float:
     if count < cfg.local_adapt_low * k:
-        return thr / cfg.local_adapt_factor
+        return f32_div(thr, cfg.local_adapt_factor)
     if count > cfg.local_adapt_high * k:
-        return thr * cfg.local_adapt_factor
+        return f32_mul(thr, cfg.local_adapt_factor)
     return thr
 
 
 def adapt_global(thr: float, total: int, k: int, cfg: OkTopkConfig) -> float:
     if total < cfg.global_adapt_low * k:
-        return thr / cfg.global_adapt_inc
+        return f32_div(thr, cfg.global_adapt_inc)
     if total > cfg.global_adapt_high * k:
-        return thr * cfg.global_adapt_dec
+        return f32_mul(thr, cfg.global_adapt_dec)
     return thr
 
 
@@ -212,6 +224,7 @@ def topka_oracle(grads, states, cfg: OkTopkConfig, density=None, reselect: bool 
         res[idx] = 0.0
         total[idx] += vals
         picks.append((idx, vals))
+        st.local_thr = float(vals.abs().min())
         st.last_local_count = k
         st.last_volume_elems = 2 * k * (P - 1) * 2 if P > 1 else 0
         st.last_mode = "topkA2" if reselect else "topkA"

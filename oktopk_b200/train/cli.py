@@ -1,0 +1,91 @@
+"""Command line (L0): one entry point for all three reference programs.
+
+    torchrun --nproc-per-node 8 --master-addr 127.0.0.1 -m oktopk_b200.train.cli \
+        --dnn vgg16 --dataset cifar10 --batch-size 16 --lr 0.1 --compression --compressor oktopk --density 0.02
+
+Flag parity with ``VGG/main_trainer.py:144-160`` (``--batch-size --nsteps-update --nworkers --nwpernode
+--compression --compressor --sigma-scale --density --dataset --dnn --data-dir --lr --max-epochs --pretrain``)
+and with the BERT driver's relevant flags (``BERT/bert/main_bert.py:645-765``: ``--train_batch_size
+--max_seq_length --num_minibatches --gradient_accumulation_steps --checkpoint_dir --config_path --module``).
+The SLURM/sbatch + ``exp_configs/*.conf`` layer of the reference becomes ``--preset`` + plain flags; launch is
+``torchrun`` (one process per GPU) instead of ``srun python -m mpi4py``.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import re
+import sys
+
+import torch
+
+
+def build_parser() -> argparse.ArgumentParser:
+    from ..compression import compressors
+    from ..models import DNNS
+    p = argparse.ArgumentParser(description="oktopk_b200 trainer")
+    p.add_argument("--batch-size", "--train_batch_size", dest="batch_size", type=int, default=16)
+    p.add_argument("--nsteps-update", "--gradient_accumulation_steps", dest="nsteps_update", type=int, default=1)
+    p.add_argument("--nworkers", type=int, default=1, help="informational: world size comes from torchrun")
+    p.add_argument("--nwpernode", type=int, default=1)
+    p.add_argument("--compression", dest="compression", action="store_true")
+    p.add_argument("--compressor", type=str, default="oktopk", choices=[k for k in compressors if k])
+    p.add_argument("--sigma-scale", type=float, default=2.5)
+    p.add_argument("--density", type=float, default=0.01)
+    p.add_argument("--dataset", type=str, default=None, choices=["imagenet", "cifar10", "an4", "ptb", "mnist", "wikipedia"])
+    p.add_argument("--dnn", type=str, default="vgg16", choices=DNNS)
+    p.add_argument("--module", type=str, default=None, help="BERT style 'models.bert12.depth=4' (layers / depth)")
+    p.add_argument("--config_path", type=str, default=None, help="BERT config json")
+    p.add_argument("--data-dir", type=str, default=None)
+    p.add_argument("--lr", type=float, default=0.1)
+    p.add_argument("--max-epochs", type=int, default=1)
+    p.add_argument("--max-iters", "--num_minibatches", dest="max_iters", type=int, default=None)
+    p.add_argument("--max_seq_length", type=int, default=128)
+    p.add_argument("--pretrain", type=str, default=None)
+    p.add_argument("--checkpoint_dir", type=str, default=None)
+    p.add_argument("--log-dir", type=str, default=None)
+    p.add_argument("--preset", type=str, default=None, help="vgg16 | lstm_an4 | bert_base (SURVEY A.1 constants)")
+    p.add_argument("--warmup-iters", type=int, default=None, help="dense warm-up iterations (preset default if omitted)")
+    p.add_argument("--bucket-elems", type=int, default=None)
+    p.add_argument("--backend", type=str, default=None, choices=["auto", "cuda", "dist"])
+    p.add_argument("--no-fused", action="store_true", help="phase-per-launch ablation of the persistent kernel")
+    p.add_argument("--deterministic", action="store_true")
+    p.add_argument("--seed", type=int, default=0)
+    return p
+
+
+def main(argv=None) -> int:
+    args = build_parser().parse_args(argv)
+    import oktopk_b200 as okt
+    from .trainer import preset_for, robust_ssgd
+    okt.init()
+    dnn = args.dnn
+    if args.module:                       # 'models.bert12.depth=4'
+        m = re.search(r"bert(\d+)\.depth=(\d+)", args.module)
+        if m:
+            dnn = "bert_base"
+    cfg = okt.preset(args.preset or preset_for(dnn), density=args.density, sigma_scale=args.sigma_scale)
+    over = {}
+    if args.warmup_iters is not None:
+        over["warmup_iters"] = args.warmup_iters
+    if args.bucket_elems is not None:
+        over["bucket_elems"] = args.bucket_elems
+    if args.no_fused:
+        over["fused"] = False
+    if args.deterministic:
+        over["deterministic"] = True
+    cfg = cfg.replace(**over)
+    tr = robust_ssgd(dnn, args.dataset, args.data_dir, okt.size(), args.lr, args.batch_size, args.nsteps_update,
+                     args.max_epochs, compression=args.compression, compressor=args.compressor,
+                     nwpernode=args.nwpernode, sigma_scale=args.sigma_scale, pretrain=args.pretrain,
+                     density=args.density, max_iters=args.max_iters, checkpoint_dir=args.checkpoint_dir, cfg=cfg,
+                     log_dir=args.log_dir, seq_len=args.max_seq_length, seed=args.seed, backend=args.backend)
+    if okt.rank() == 0:
+        print("final loss %.5f after %d iterations" % (tr.last_loss(), tr.train_iter))
+    tr.close()
+    okt.shutdown()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

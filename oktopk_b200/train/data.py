@@ -1,0 +1,196 @@
+"""Data pipelines: synthetic generators of every dataset shape the reference trains on, with the
+same sharding semantics (``DistributedSampler`` when world > 1, ``VGG/dl_trainer.py:312-467``), plus
+optional real-data loaders when the files are already on disk (there is no network here).
+
+Shapes: CIFAR-10 ``[B,3,32,32]``/10 classes, ImageNet ``[B,3,224,224]``/1000, MNIST ``[B,1,28,28]``,
+AN4 spectrograms ``[B,1,161,T]`` + transcripts for CTC (the reference's ``audio_data`` loader is
+missing from its repo), PTB ``[35,B]`` token windows, Wikipedia-shaped BERT pre-training
+features ``input_ids/segment_ids/input_mask/lm_label_ids [B,128]`` + ``is_next [B]``
+(``BERT/bert/main_bert.py:535-639``).
+
+Batches are produced in pinned host memory; ``Prefetcher`` moves them to the device on a side stream
+(H2D overlapped with compute) -- the reference does a synchronous ``.cuda()`` per step.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Iterator, List, Optional, Tuple
+
+import torch
+from torch.utils.data import DataLoader, Dataset, DistributedSampler
+
+DATASET_CLASSES = {"cifar10": 10, "imagenet": 1000, "mnist": 10, "an4": 29, "ptb": 10000, "wikipedia": 30522}
+
+
+class SyntheticImages(Dataset):
+    def __init__(self, n: int, shape: Tuple[int, int, int], classes: int, seed: int = 0):
+        g = torch.Generator().manual_seed(seed)
+        self.n, self.shape, self.classes = n, shape, classes
+        # a small pool of distinct images re-indexed cyclically keeps host memory bounded
+        self.pool = torch.randn((min(n, 2048),) + shape, generator=g)
+        self.labels = torch.randint(0, classes, (n,), generator=g)
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        return self.pool[i % self.pool.size(0)], self.labels[i]
+
+
+class SyntheticAN4(Dataset):
+    """Variable-length spectrogram + transcript pairs (AN4: ~1-5 s utterances, 161 frequency bins)."""
+
+    def __init__(self, n: int = 948, min_frames: int = 100, max_frames: int = 400, seed: int = 0, labels: int = 29):
+        g = torch.Generator().manual_seed(seed)
+        self.n = n
+        self.frames = torch.randint(min_frames, max_frames + 1, (n,), generator=g)
+        self.tlen = torch.clamp(self.frames // 12, min=2)
+        self.seed, self.labels = seed, labels
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        g = torch.Generator().manual_seed(self.seed * 1_000_003 + i)
+        spect = torch.randn(161, int(self.frames[i]), generator=g)
+        target = torch.randint(1, self.labels, (int(self.tlen[i]),), generator=g)
+        return spect, target
+
+
+def an4_collate(batch):
+    """Sort by length (longest first), pad spectrograms, concatenate targets (deepspeech convention)."""
+    batch = sorted(batch, key=lambda s: s[0].size(1), reverse=True)
+    T = batch[0][0].size(1)
+    B = len(batch)
+    inputs = torch.zeros(B, 1, 161, T)
+    in_pct = torch.empty(B)
+    tsizes = torch.empty(B, dtype=torch.int32)
+    targets = []
+    for i, (sp, tg) in enumerate(batch):
+        inputs[i, 0, :, :sp.size(1)] = sp
+        in_pct[i] = sp.size(1) / float(T)
+        tsizes[i] = tg.numel()
+        targets.append(tg)
+    return inputs, torch.cat(targets).int(), in_pct, tsizes
+
+
+class SyntheticPTB(Dataset):
+    def __init__(self, n_tokens: int = 929_589, vocab: int = 10000, batch_size: int = 20, num_steps: int = 35, seed: int = 0):
+        g = torch.Generator().manual_seed(seed)
+        self.data = torch.randint(0, vocab, (n_tokens,), generator=g)
+        self.num_steps = num_steps
+        self.n = (n_tokens - 1) // num_steps
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        s = i * self.num_steps
+        return self.data[s:s + self.num_steps], self.data[s + 1:s + 1 + self.num_steps]
+
+
+class SyntheticWikipedia(Dataset):
+    def __init__(self, n: int = 100_000, seq: int = 128, vocab: int = 30522, seed: int = 0):
+        self.n, self.seq, self.vocab, self.seed = n, seq, vocab, seed
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        from ..models.bert import synthetic_batch
+        g = torch.Generator().manual_seed(self.seed * 7_000_003 + i)
+        ids, seg, mask, labels, nxt = synthetic_batch(1, self.seq, self.vocab, generator=g)
+        return ids[0], seg[0], mask[0], labels[0], nxt[0]
+
+
+def build_dataset(name: str, data_dir: Optional[str] = None, train: bool = True, seed: int = 0, **kw) -> Dataset:
+    """Real data if it is already on disk under ``data_dir`` (never downloads), else synthetic."""
+    name = name.lower()
+    if data_dir and name in ("cifar10", "mnist"):
+        try:
+            import torchvision
+            import torchvision.transforms as T
+            if name == "cifar10":
+                tf = T.Compose(([T.RandomCrop(32, padding=4), T.RandomHorizontalFlip()] if train else []) +
+                               [T.ToTensor(), T.Normalize((0.4914, 0.4822, 0.4465), (0.2023, 0.1994, 0.2010))])
+                return torchvision.datasets.CIFAR10(data_dir, train=train, download=False, transform=tf)
+            tf = T.Compose([T.ToTensor(), T.Normalize((0.1307,), (0.3081,))])
+            return torchvision.datasets.MNIST(data_dir, train=train, download=False, transform=tf)
+        except Exception:  # noqa: BLE001 - fall back to synthetic
+            pass
+    if name == "cifar10":
+        return SyntheticImages(50_000 if train else 10_000, (3, 32, 32), 10, seed)
+    if name == "imagenet":
+        return SyntheticImages(kw.get("n", 12_800), (3, 224, 224), 1000, seed)
+    if name == "mnist":
+        return SyntheticImages(60_000 if train else 10_000, (1, 28, 28), 10, seed)
+    if name == "an4":
+        return SyntheticAN4(948 if train else 130, seed=seed)
+    if name == "ptb":
+        return SyntheticPTB(seed=seed, **{k: v for k, v in kw.items() if k in ("batch_size", "num_steps")})
+    if name in ("wikipedia", "bert"):
+        return SyntheticWikipedia(seq=kw.get("seq", 128), seed=seed)
+    raise ValueError("unknown dataset %r" % name)
+
+
+def build_loader(dataset: Dataset, name: str, batch_size: int, rank: int, world: int, train: bool = True,
+                 num_workers: int = 0, seed: int = 0):
+    sampler = DistributedSampler(dataset, num_replicas=world, rank=rank, shuffle=train, seed=seed) if world > 1 else None
+    collate = an4_collate if name == "an4" else None
+    loader = DataLoader(dataset, batch_size=batch_size, shuffle=(train and sampler is None), sampler=sampler,
+                        num_workers=num_workers, pin_memory=torch.cuda.is_available(), drop_last=train, collate_fn=collate)
+    return loader, sampler
+
+
+class Prefetcher:
+    """Endless iterator over a DataLoader that stages the next batch on the device from pinned memory
+    on a side stream (H2D overlaps the previous step)."""
+
+    def __init__(self, loader: DataLoader, device: torch.device, sampler=None):
+        self.loader, self.device, self.sampler = loader, device, sampler
+        self.epoch = 0
+        self.it: Optional[Iterator] = None
+        self.stream = torch.cuda.Stream() if device.type == "cuda" else None
+        self.next_batch = None
+        self.h2d_bytes = 0
+        self._preload()
+
+    def _raw_next(self):
+        if self.it is None:
+            if self.sampler is not None:
+                self.sampler.set_epoch(self.epoch)
+            self.it = iter(self.loader)
+        try:
+            return next(self.it)
+        except StopIteration:
+            self.epoch += 1
+            self.it = None
+            return self._raw_next()
+
+    def _preload(self):
+        batch = self._raw_next()
+        if self.stream is None:
+            self.next_batch = batch
+            return
+        with torch.cuda.stream(self.stream):
+            out = []
+            for t in batch:
+                if torch.is_tensor(t):
+                    if not t.is_pinned():
+                        t = t.pin_memory()
+                    self.h2d_bytes += t.numel() * t.element_size()
+                    out.append(t.to(self.device, non_blocking=True))
+                else:
+                    out.append(t)
+            self.next_batch = tuple(out)
+
+    def next(self):
+        if self.stream is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        batch = self.next_batch
+        if self.stream is not None:
+            for t in batch:
+                if torch.is_tensor(t):
+                    t.record_stream(torch.cuda.current_stream())
+        self._preload()
+        return batch

@@ -1,0 +1,1 @@
+"""Utilities: logging, metrics/timers/NVTX, CTC decoding + WER, analytic perf models, settings, elastic helpers."""

@@ -1,0 +1,136 @@
+"""Multi-GPU tests (>= 2 devices): the fused peer-memory kernels across real NVLink peers versus the
+single-process oracle.  At P=2 the sparse reduction is bitwise reproducible (a+b == b+a), so results,
+residuals, thresholds and region boundaries must match the oracle exactly."""
+import os
+import sys
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from mp_util import run_distributed  # noqa: E402
+
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+
+
+def _grad(it, rank, n):
+    g = torch.Generator().manual_seed(1000 * it + rank)
+    x = torch.randn(n, generator=g)
+    # non-uniform magnitude profile so that balanced regions differ from uniform ones
+    ramp = torch.linspace(0.2, 2.0, n)
+    return x * ramp
+
+
+def _engine_worker(rank, P, name, n, iters, cfg_kw):
+    from oktopk_b200.config import OkTopkConfig
+    from oktopk_b200.parallel.gpu_engine import CudaBucketEngine
+    from oktopk_b200.parallel.world import World
+    w = World()
+    cfg = OkTopkConfig(**cfg_kw)
+    eng = CudaBucketEngine(n, cfg, w, name="t")
+    outs, stats = [], []
+    for it in range(iters):
+        eng.grad.copy_(_grad(it, rank, n).cuda())
+        torch.cuda.synchronize()
+        w.barrier()
+        eng.reduce(name)
+        torch.cuda.synchronize()
+        outs.append(eng.grad.cpu().clone())
+        stats.append(eng.stats())
+    res = eng.residual.cpu().clone()
+    w.barrier()
+    eng.close()
+    return outs, res, stats
+
+
+def _check(name, P, n, iters, cfg_kw, exact=True):
+    from oktopk_b200.config import OkTopkConfig
+    from oktopk_b200.parallel.oracle import run_oracle
+    from oktopk_b200.parallel.state import SparseState
+    got = run_distributed(_engine_worker, P, (name, n, iters, cfg_kw), backend="nccl", timeout=600)
+    cfg = OkTopkConfig(**cfg_kw)
+    states = [SparseState(n, P) for _ in range(P)]
+    for it in range(iters):
+        ref = run_oracle(name, [_grad(it, r, n) for r in range(P)], states, cfg)
+        for r in range(P):
+            out = got[r][0][it]
+            if exact:
+                bad = int((out != ref[r]).sum())
+                assert bad == 0, "%s it %d rank %d: %d mismatches, stats %s" % (name, it, r, bad, got[r][2][it])
+                assert got[r][2][it]["edges"] == states[r].region_offsets + [n], (it, got[r][2][it]["edges"], states[r].region_offsets)
+            else:
+                torch.testing.assert_close(out, ref[r], rtol=1e-5, atol=1e-6)
+            assert got[r][2][it]["overflow_send"] == 0 and got[r][2][it]["overflow_gather"] == 0
+    if exact and states[0].residual is not None:
+        for r in range(P):
+            assert int((got[r][1] != states[r].residual).sum()) == 0, "residual mismatch rank %d" % r
+    return got
+
+
+@pytest.mark.parametrize("pull", ["tma", "ldg"])
+def test_oktopk_two_gpus_matches_oracle(pull):
+    kw = dict(density=0.01, local_recompute_interval=4, global_recompute_interval=4, repartition_interval=4, pull_mode=pull,
+              slot_factor=64, gather_factor=64)
+    got = _check("oktopk", 2, 1_000_000, 10, kw)
+    # communication volume of the threshold-reuse iterations stays under the 6k(P-1)/P bound (+ slack for k drift)
+    k = 10_000
+    for it in (0, 4, 8):
+        assert got[0][2][it]["volume_elems"] <= 2 * 6 * k, got[0][2][it]
+
+
+def test_oktopk_two_gpus_unfused_and_deterministic():
+    kw = dict(density=0.02, local_recompute_interval=3, global_recompute_interval=5, repartition_interval=2,
+              fused=False, deterministic=True, slot_factor=64, gather_factor=64)
+    _check("oktopk", 2, 300_000, 7, kw)
+
+
+@pytest.mark.parametrize("name", ["topkSA", "gaussiankSA", "topkA", "topkAopt", "topkA2", "gtopk", "none"])
+def test_baseline_schemes_two_gpus_match_oracle(name):
+    kw = dict(density=0.01, topkaopt_recompute_interval=3, slot_factor=64, gather_factor=64)
+    _check(name, 2, 400_000, 4, kw)
+
+
+def test_gaussiank_two_gpus_close():
+    from oktopk_b200.config import OkTopkConfig
+    got = run_distributed(_engine_worker, 2, ("gaussiank", 400_000, 3, dict(density=0.01, slot_factor=64, gather_factor=64)), backend="nccl", timeout=600)
+    # both ranks must hold the identical result
+    for it in range(3):
+        assert torch.equal(got[0][0][it], got[1][0][it])
+        nnz = int((got[0][0][it] != 0).sum())
+        assert 0.5 * 4000 < nnz < 3 * 2 * 4000, nnz
+
+
+def _opt_worker(rank, P, compressor, steps):
+    import oktopk_b200 as okt
+    from oktopk_b200.models import create_net
+    okt.init()
+    torch.manual_seed(0)
+    net, _ = create_net(10, "resnet20")
+    net = net.cuda()
+    okt.broadcast_parameters(net)
+    cfg = okt.preset("vgg16", density=0.02, warmup_iters=2, bucket_elems=100_000)     # several buckets -> overlap path
+    opt = okt.DistributedOptimizer(torch.optim.SGD(net.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4),
+                                   named_parameters=net.named_parameters(), compression=okt.compressors[compressor],
+                                   is_sparse=compressor != "none", cfg=cfg)
+    torch.manual_seed(100 + rank)
+    x = torch.randn(16, 3, 32, 32, device="cuda"); y = torch.randint(0, 10, (16,), device="cuda")
+    losses = []
+    for it in range(steps):
+        opt.zero_grad()
+        loss = torch.nn.functional.cross_entropy(net(x), y)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    torch.cuda.synchronize()
+    chk = float(sum(p.double().sum() for p in net.parameters()))
+    nb = len(opt._buckets)
+    opt.close()
+    return losses, chk, nb
+
+
+@pytest.mark.parametrize("compressor", ["oktopk", "none"])
+def test_distributed_optimizer_two_gpus_replicas_stay_identical(compressor):
+    r = run_distributed(_opt_worker, 2, (compressor, 12), backend="nccl", timeout=600)
+    assert r[0][2] > 1
+    assert r[0][1] == r[1][1], "replicas diverged: %r vs %r" % (r[0][1], r[1][1])
+    assert r[0][0][-1] < r[0][0][0]
