@@ -65,8 +65,8 @@ class OkTopkConfig:
     backend: str = "auto"               # 'auto' | 'cuda' (fused peer-memory kernels) | 'dist' (torch.distributed ops)
     fused: bool = True                  # one persistent kernel per bucket (False => phase-per-launch ablation)
     deterministic: bool = False         # fixed source order in the sparse reduce (bitwise run-to-run)
-    slot_factor: float = 8.0            # per-(src,dst) slot capacity = slot_factor * k / P (+ pad)
-    gather_factor: float = 8.0          # allgather slot capacity = gather_factor * k / P (+ pad)
+    slot_factor: float = 64.0           # per-(src,dst) slot capacity = slot_factor * k / P (+ pad)
+    gather_factor: float = 64.0         # allgather slot capacity = gather_factor * k / P (+ pad)
     comm_ctas: int = 0                  # CTAs of the persistent kernel (0 => 1 per SM)
     pull_mode: str = "tma"              # 'tma' (cp.async.bulk of remote chunks) | 'ldg' (128-bit peer loads)
     overlap: bool = True                # launch a bucket's exchange as soon as its last grad lands

@@ -54,8 +54,14 @@ class CudaBucketEngine:
             dmax = max(dmax, max(cfg.dynamic_densities))
         kmax = max(int(self.n * dmax), 1)
         chunk = C.CHUNK
-        self.cap = _round_up(max(cfg.slot_factor * kmax / self.P, chunk), chunk) + chunk
-        self.gcap = _round_up(max(cfg.gather_factor * kmax / self.P, 2 * kmax, chunk), chunk) + chunk
+        # Slot capacities.  The reference sizes its receive buffers from host-side count handshakes and can
+        # therefore ship arbitrarily over-selected sets (stale thresholds early in training select many times
+        # k); fixed-capacity peer-visible slots must cover that, so the default factors are generous
+        # (HBM is 180 GB) and never exceed the bucket itself.  Entries beyond the capacity are dropped and
+        # stay in the residual (counted in stats()['overflow_*']).
+        nmax = _round_up(self.n, chunk)
+        self.cap = min(nmax, _round_up(max(cfg.slot_factor * kmax / self.P, chunk), chunk)) + chunk
+        self.gcap = min(nmax, _round_up(max(cfg.gather_factor * kmax / self.P, 2 * kmax, chunk), chunk)) + chunk
         info = C.layout_info(self.P, self.cap, self.gcap)
         self.layout = info
         self.grid = C.max_coop_grid(self.device.index)

@@ -138,7 +138,7 @@ def build_loader(dataset: Dataset, name: str, batch_size: int, rank: int, world:
     sampler = DistributedSampler(dataset, num_replicas=world, rank=rank, shuffle=train, seed=seed) if world > 1 else None
     collate = an4_collate if name == "an4" else None
     loader = DataLoader(dataset, batch_size=batch_size, shuffle=(train and sampler is None), sampler=sampler,
-                        num_workers=num_workers, pin_memory=torch.cuda.is_available(), drop_last=train, collate_fn=collate)
+                        num_workers=num_workers, pin_memory=False, drop_last=train, collate_fn=collate)
     return loader, sampler
 
 
@@ -153,6 +153,8 @@ class Prefetcher:
         self.stream = torch.cuda.Stream() if device.type == "cuda" else None
         self.next_batch = None
         self.h2d_bytes = 0
+        self._pinned = {}
+        self._ring = 0
         self._preload()
 
     def _raw_next(self):
@@ -172,14 +174,21 @@ class Prefetcher:
         if self.stream is None:
             self.next_batch = batch
             return
+        # stage through a small ring of reusable pinned buffers (no per-step cudaHostAlloc, no pin thread)
+        self._ring = (self._ring + 1) % 3
         with torch.cuda.stream(self.stream):
             out = []
-            for t in batch:
+            for j, t in enumerate(batch):
                 if torch.is_tensor(t):
-                    if not t.is_pinned():
-                        t = t.pin_memory()
+                    key = (self._ring, j)
+                    buf = self._pinned.get(key)
+                    if buf is None or buf.numel() < t.numel() or buf.dtype != t.dtype:
+                        buf = torch.empty(max(t.numel(), 1), dtype=t.dtype).pin_memory()
+                        self._pinned[key] = buf
+                    host = buf[:t.numel()].view(t.shape)
+                    host.copy_(t)
                     self.h2d_bytes += t.numel() * t.element_size()
-                    out.append(t.to(self.device, non_blocking=True))
+                    out.append(host.to(self.device, non_blocking=True))
                 else:
                     out.append(t)
             self.next_batch = tuple(out)
