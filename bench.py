@@ -104,6 +104,7 @@ def parse_args(argv=None):
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--backend", type=str, default=None)
     p.add_argument("--bucket-elems", type=int, default=None)
+    p.add_argument("--no-graph", action="store_true", help="disable whole-step CUDA graphs (eager launches)")
     return p.parse_args(argv)
 
 
@@ -127,7 +128,7 @@ def run_ours(args) -> dict:
     cfg = okt.preset(preset, **over)
     tr = Trainer(dnn=dnn, dataset=dataset, batch_size=bs, lr=lr, compressor=args.compressor, density=args.density,
                  compression=args.compressor != "none", cfg=cfg, world=w, seq_len=args.seq_len, backend=args.backend,
-                 t_total=100000, warmup=0.1)
+                 t_total=100000, warmup=0.1, cuda_graph=not args.no_graph)
     dev = tr.device
 
     def sync_all():
@@ -141,8 +142,13 @@ def run_ours(args) -> dict:
     torch.cuda.synchronize()
 
     def step_resident(i):
-        tr.optimizer.zero_grad()
         tr.net.train()
+        if tr.graphed is not None and tr.graphed.enabled:
+            tr.adjust_learning_rate()
+            loss = tr.graphed.step(pool[i % len(pool)])
+            tr._bookkeep_iter()
+            return loss
+        tr.optimizer.zero_grad()
         loss, _ = tr._forward_loss(pool[i % len(pool)])
         loss.backward()
         tr.update_model()
@@ -208,6 +214,9 @@ def run_ours(args) -> dict:
                    "l2": "no explicit flush: params+grads+residual+momentum working set %.0f MB vs 126 MB L2" % working_set_mb,
                    "buckets": len(stats)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+        "cuda_graph": (None if tr.graphed is None else {"enabled": tr.graphed.enabled, "graphs": len(tr.graphed.graphs),
+                                                        "why_disabled": tr.graphed.why_disabled}),
+        "final_loss": tr.last_loss(),
         "comm": {k: {kk: v[kk] for kk in ("mode", "local_count", "global_count", "volume_elems", "overflow_send",
                                           "overflow_gather") if kk in v} for k, v in stats.items()},
     }

@@ -185,14 +185,17 @@ static void kth_abs(uint64_t x, int n, int k, uint64_t st, uint64_t out, int gri
 }
 
 static void fused_sgd(uint64_t p, uint64_t g, uint64_t mom, int n, double lr, double momentum, double dampening,
-                      double wd, int nesterov, int first, int zero_grad, double grad_scale, uint64_t stream) {
+                      double wd, int nesterov, int first, int zero_grad, double grad_scale, uint64_t stream,
+                      uint64_t lr_ptr) {
     ck(launch_fused_sgd(P_<float>(p), P_<float>(g), P_<float>(mom), n, (float)lr, (float)momentum, (float)dampening,
-                        (float)wd, nesterov, first, zero_grad, (float)grad_scale, S_(stream)), "fused_sgd");
+                        (float)wd, nesterov, first, zero_grad, (float)grad_scale, P_<float>(lr_ptr), S_(stream)),
+       "fused_sgd");
 }
 static void fused_bert_adam(uint64_t p, uint64_t g, uint64_t m, uint64_t v, int n, double lr, double b1, double b2,
-                            double eps, double wd, int zero_grad, uint64_t stream) {
+                            double eps, double wd, int zero_grad, uint64_t stream, uint64_t lr_ptr) {
     ck(launch_fused_bert_adam(P_<float>(p), P_<float>(g), P_<float>(m), P_<float>(v), n, (float)lr, (float)b1,
-                              (float)b2, (float)eps, (float)wd, zero_grad, S_(stream)), "fused_bert_adam");
+                              (float)b2, (float)eps, (float)wd, zero_grad, P_<float>(lr_ptr), S_(stream)),
+       "fused_bert_adam");
 }
 static void momentum_correct(uint64_t g, uint64_t buf, int n, double momentum, uint64_t stream) {
     ck(launch_momentum_correct(P_<float>(g), P_<float>(buf), n, (float)momentum, S_(stream)), "momentum_correct");
@@ -220,8 +223,12 @@ PYBIND11_MODULE(_C, m) {
     m.def("gather_run", &gather_run);
     m.def("dense_run", &dense_run);
     m.def("kth_abs", &kth_abs);
-    m.def("fused_sgd", &fused_sgd);
-    m.def("fused_bert_adam", &fused_bert_adam);
+    m.def("fused_sgd", &fused_sgd, py::arg("p"), py::arg("g"), py::arg("mom"), py::arg("n"), py::arg("lr"),
+          py::arg("momentum"), py::arg("dampening"), py::arg("wd"), py::arg("nesterov"), py::arg("first"),
+          py::arg("zero_grad"), py::arg("grad_scale"), py::arg("stream"), py::arg("lr_ptr") = 0);
+    m.def("fused_bert_adam", &fused_bert_adam, py::arg("p"), py::arg("g"), py::arg("m"), py::arg("v"), py::arg("n"),
+          py::arg("lr"), py::arg("b1"), py::arg("b2"), py::arg("eps"), py::arg("wd"), py::arg("zero_grad"),
+          py::arg("stream"), py::arg("lr_ptr") = 0);
     m.def("momentum_correct", &momentum_correct);
     m.def("clip_by_norm", &clip_by_norm);
     m.attr("MAXP") = OKT_MAXP;

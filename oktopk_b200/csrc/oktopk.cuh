@@ -151,9 +151,10 @@ cudaError_t launch_dense_allreduce(const DenseParams& p, int grid, cudaStream_t 
 cudaError_t launch_kth_abs(const float* x, int n, int k, OktState* st, float* out_thr, int grid, cudaStream_t stream);
 cudaError_t launch_fused_sgd(float* p, float* g, float* mom, int n, float lr, float momentum, float dampening,
                              float weight_decay, int nesterov, int first_step, int zero_grad, float grad_scale,
-                             cudaStream_t stream);
+                             const float* lr_ptr, cudaStream_t stream);
 cudaError_t launch_fused_bert_adam(float* p, float* g, float* m, float* v, int n, float lr, float b1, float b2,
-                                   float eps, float weight_decay, int zero_grad, cudaStream_t stream);
+                                   float eps, float weight_decay, int zero_grad, const float* lr_ptr,
+                                   cudaStream_t stream);
 cudaError_t launch_momentum_correct(float* g, float* buf, int n, float momentum, cudaStream_t stream);
 cudaError_t launch_l2norm_sq(const float* x, int n, float* out, cudaStream_t stream);
 cudaError_t launch_scale(float* x, int n, const float* norm_sq, float max_norm, cudaStream_t stream);

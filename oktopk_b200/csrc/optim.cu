@@ -15,7 +15,8 @@ __global__ void __launch_bounds__(kOptThreads) fused_sgd_kernel(float* __restric
                                                                  float* __restrict__ mom, int n, float lr,
                                                                  float momentum, float dampening, float wd,
                                                                  int nesterov, int first, int zero_grad,
-                                                                 float grad_scale) {
+                                                                 float grad_scale, const float* __restrict__ lr_ptr) {
+    if (lr_ptr) lr = *lr_ptr;            // device-resident learning rate: the launch is CUDA-graph replayable
     const int n4 = n >> 2;
     float4* p4 = reinterpret_cast<float4*>(p);
     float4* g4 = reinterpret_cast<float4*>(g);
@@ -53,7 +54,9 @@ __global__ void __launch_bounds__(kOptThreads) fused_sgd_kernel(float* __restric
 __global__ void __launch_bounds__(kOptThreads) fused_bert_adam_kernel(float* __restrict__ p, float* __restrict__ g,
                                                                        float* __restrict__ m, float* __restrict__ v,
                                                                        int n, float lr, float b1, float b2, float eps,
-                                                                       float wd, int zero_grad) {
+                                                                       float wd, int zero_grad,
+                                                                       const float* __restrict__ lr_ptr) {
+    if (lr_ptr) lr = *lr_ptr;
     const int n4 = n >> 2;
     float4* p4 = reinterpret_cast<float4*>(p);
     float4* g4 = reinterpret_cast<float4*>(g);
@@ -128,16 +131,17 @@ static inline int opt_grid(int n) {
 
 cudaError_t launch_fused_sgd(float* p, float* g, float* mom, int n, float lr, float momentum, float dampening,
                              float weight_decay, int nesterov, int first_step, int zero_grad, float grad_scale,
-                             cudaStream_t stream) {
+                             const float* lr_ptr, cudaStream_t stream) {
     fused_sgd_kernel<<<opt_grid(n), kOptThreads, 0, stream>>>(p, g, mom, n, lr, momentum, dampening, weight_decay,
-                                                             nesterov, first_step, zero_grad, grad_scale);
+                                                             nesterov, first_step, zero_grad, grad_scale, lr_ptr);
     return cudaGetLastError();
 }
 
 cudaError_t launch_fused_bert_adam(float* p, float* g, float* m, float* v, int n, float lr, float b1, float b2,
-                                   float eps, float weight_decay, int zero_grad, cudaStream_t stream) {
+                                   float eps, float weight_decay, int zero_grad, const float* lr_ptr,
+                                   cudaStream_t stream) {
     fused_bert_adam_kernel<<<opt_grid(n), kOptThreads, 0, stream>>>(p, g, m, v, n, lr, b1, b2, eps, weight_decay,
-                                                                   zero_grad);
+                                                                   zero_grad, lr_ptr);
     return cudaGetLastError();
 }
 

@@ -79,6 +79,40 @@ class _BucketedComm:
                 self._hook_handles.append(p.register_post_accumulate_grad_hook(self._make_hook(p)))
         if self._use_streams:
             self._comm_stream = torch.cuda.Stream()
+        # device-resident learning rates (one float per param group): the fused update kernels read lr from
+        # memory so that a captured CUDA graph of the whole step stays valid when the schedule moves
+        self._lr_dev = None
+        self._lr_pin, self._lr_ring, self._lr_last = [], 0, None
+        dev0 = self._buckets[0].params[0].device if self._buckets else torch.device("cpu")
+        if dev0.type == "cuda" and ext.available():
+            G = len(self.param_groups)
+            self._lr_dev = torch.zeros(max(G, 1), dtype=torch.float32, device=dev0)
+            self._lr_pin = [torch.zeros(max(G, 1), dtype=torch.float32).pin_memory() for _ in range(4)]
+
+    def _group_lr(self, gi: int) -> float:
+        return float(self.param_groups[gi]["lr"])
+
+    def refresh_lr(self) -> None:
+        """Push the current per-group learning rates to the device (one tiny async H2D, only when changed).
+        Never called while a stream is capturing: graph replays call it right before ``replay()``."""
+        if self._lr_dev is None:
+            return
+        vals = [self._group_lr(gi) for gi in range(len(self.param_groups))]
+        if vals == self._lr_last:
+            return
+        self._lr_ring = (self._lr_ring + 1) % len(self._lr_pin)
+        pin = self._lr_pin[self._lr_ring]
+        for i, v in enumerate(vals):
+            pin[i] = v
+        self._lr_dev.copy_(pin, non_blocking=True)
+        self._lr_last = vals
+
+    def _lr_ptr(self, gi: int) -> int:
+        return 0 if self._lr_dev is None else self._lr_dev.data_ptr() + 4 * gi
+
+    def _maybe_refresh_lr(self) -> None:
+        if self._lr_dev is not None and not torch.cuda.is_current_stream_capturing():
+            self.refresh_lr()
 
     # ------------------------------------------------------------------ hooks
     def _make_hook(self, p):
@@ -192,7 +226,7 @@ class _BucketedComm:
             if use_kernel:
                 ext.require().fused_sgd(b.flat_param.data_ptr() + 4 * s, b.grad.data_ptr() + 4 * s,
                                         mom.data_ptr() + 4 * s, e - s, lr, m, damp, wd, int(nest), int(first), 1, 1.0,
-                                        torch.cuda.current_stream().cuda_stream)
+                                        torch.cuda.current_stream().cuda_stream, self._lr_ptr(gi))
             else:
                 gs, ms = b.grad[s:e], mom[s:e]
                 if b.flat_param is not None:
@@ -228,6 +262,7 @@ class _DistributedOptimizerMixin(_BucketedComm):
         if not self.local:
             self.synchronize()
         if self._okt_is_sgd:
+            self._maybe_refresh_lr()
             with torch.no_grad():
                 for b in self._buckets:
                     self._fused_sgd(b)
@@ -381,6 +416,9 @@ class BertAdam(_BucketedComm, torch.optim.Optimizer):
                         cfg=base.replace(density=density), world=world, backend=backend)
         self._okt_setup(named_parameters, ar, flatten_params=flatten_params)
 
+    def _group_lr(self, gi: int) -> float:
+        return float(self._scheduled_lr(self.param_groups[gi], self.counter))
+
     def get_lr(self) -> List[float]:
         out = []
         for g in self.param_groups:
@@ -400,6 +438,7 @@ class BertAdam(_BucketedComm, torch.optim.Optimizer):
                 loss = closure()
         if not self.local:
             self.synchronize()
+        self._maybe_refresh_lr()
         with torch.no_grad():
             for b in self._buckets:
                 self._fused_adam(b)
@@ -429,7 +468,8 @@ class BertAdam(_BucketedComm, torch.optim.Optimizer):
             if use_kernel:
                 ext.require().fused_bert_adam(b.flat_param.data_ptr() + 4 * s, b.grad.data_ptr() + 4 * s,
                                               m.data_ptr() + 4 * s, v.data_ptr() + 4 * s, e - s, lr, g["b1"], g["b2"],
-                                              g["e"], g["weight_decay"], 1, torch.cuda.current_stream().cuda_stream)
+                                              g["e"], g["weight_decay"], 1, torch.cuda.current_stream().cuda_stream,
+                                              self._lr_ptr(gi))
             else:
                 gs, ms, vs = b.grad[s:e], m[s:e], v[s:e]
                 ms.mul_(g["b1"]).add_(gs, alpha=1 - g["b1"])

@@ -48,7 +48,7 @@ class Trainer:
                  cfg: Optional[OkTopkConfig] = None, world: Optional[World] = None, device: Optional[torch.device] = None,
                  seed: int = 0, prefix: str = "run", log_dir: Optional[str] = None, num_workers: int = 0,
                  seq_len: int = 128, t_total: int = -1, warmup: float = -1, pretrain: Optional[str] = None,
-                 norm_clip: Optional[float] = None, backend: Optional[str] = None):
+                 norm_clip: Optional[float] = None, backend: Optional[str] = None, cuda_graph: bool = False):
         self.world = world or _world()
         self.rank, self.nworkers = self.world.rank, self.world.size
         self.dnn = dnn
@@ -112,6 +112,11 @@ class Trainer:
         self.hidden = None
         self.sparsities: List[float] = []
         self._iter_times: List[float] = []
+        # whole-step CUDA graphs (fixed-shape workloads only; AN4 batches vary in length, PTB carries hidden state)
+        self.graphed = None
+        if cuda_graph and self.device.type == "cuda" and self.dataset not in ("an4", "ptb") and nsteps_update == 1:
+            from .graph_step import GraphedTrainStep
+            self.graphed = GraphedTrainStep(self)
 
     # ------------------------------------------------------------------ LR schedules
     def adjust_learning_rate(self) -> float:
@@ -193,8 +198,21 @@ class Trainer:
             torch.nn.utils.clip_grad_norm_(self.net.parameters(), 0.25)
         self.optimizer.step()
 
+    def _bookkeep_iter(self) -> None:
+        self.loss_n += 1
+        if self.train_iter % self.iters_per_epoch == self.iters_per_epoch - 1:
+            self.train_epoch += 1
+            self.optimizer.add_train_epoch()
+        self.train_iter += 1
+
     def train_step(self) -> None:
         """One optimizer update = ``nsteps_update`` micro-steps (``VGG/main_trainer.py:83-100``)."""
+        if self.graphed is not None and self.graphed.enabled:
+            self.net.train()
+            self.adjust_learning_rate()
+            self._last_loss = self.graphed.step(self.prefetch.next())
+            self._bookkeep_iter()
+            return
         self.optimizer.zero_grad()
         for j in range(self.nsteps_update):
             self.optimizer.local = j < self.nsteps_update - 1

@@ -93,7 +93,8 @@ def _run_engine_vs_oracle(name, n, iters, cfg, tol_count=0):
         assert rbad <= tol_count, "%s it %d: residual mismatch %d" % (name, it, rbad)
         if tol_count == 0:
             assert st["local_count"] == states[0].last_local_count, (it, st, states[0].last_local_count)
-            assert abs(st["local_thr"] - states[0].local_thr) <= 1e-12 + 1e-7 * abs(states[0].local_thr)
+            if name in ("oktopk", "topkAopt"):       # schemes whose threshold is carried across iterations
+                assert abs(st["local_thr"] - states[0].local_thr) <= 1e-12 + 1e-7 * abs(states[0].local_thr)
         assert st["overflow_send"] == 0 and st["overflow_gather"] == 0
     eng.close()
 
