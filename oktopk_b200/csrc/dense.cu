@@ -14,6 +14,8 @@
 namespace okt {
 
 constexpr int kDenseThreads = 512;
+constexpr int kDenseTile = 2;
+constexpr int kSrcGroup = 8;
 
 __device__ __forceinline__ void cta_peer_barrier(const DenseParams& p, int phase, uint64_t ticket) {
     // flag block layout per rank: uint64 [2 phases][gridDim.x][OKT_MAXP]
@@ -44,19 +46,47 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_allreduce_kernel(const
     const int lo = rank * shard4;
     const int hi = min(n4, lo + shard4);
     const float scale = p.scale;
-    for (int v = lo + blockIdx.x * kDenseThreads + threadIdx.x; v < hi; v += gridDim.x * kDenseThreads) {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    // kDenseTile vectors per thread per trip and all P peer loads of a vector issued back to back: NVLink
+    // round trips are ~2-3 us, so bandwidth is bought with bytes in flight (512 thr x 2 x P x 16 B per SM).
+    const int trip = gridDim.x * kDenseThreads * kDenseTile;
+    for (int base = lo + blockIdx.x * kDenseThreads * kDenseTile; base < hi; base += trip) {
+        float4 accs[kDenseTile];
+#pragma unroll
+        for (int u = 0; u < kDenseTile; ++u) accs[u] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
-        for (int s = 0; s < P; ++s) {             // fixed rank order: every rank computes bitwise the same sum
-            const int4 raw = ld_peer_i4(reinterpret_cast<const int4*>(p.bufs[s]) + v);
-            acc.x += __int_as_float(raw.x); acc.y += __int_as_float(raw.y);
-            acc.z += __int_as_float(raw.z); acc.w += __int_as_float(raw.w);
+        for (int s0 = 0; s0 < P; s0 += kSrcGroup) {      // sources in groups of 8 (register budget), fixed order
+            int4 raw[kDenseTile][kSrcGroup];
+#pragma unroll
+            for (int u = 0; u < kDenseTile; ++u) {
+                const int v = base + u * kDenseThreads + threadIdx.x;
+                if (v < hi) {
+#pragma unroll
+                    for (int s = 0; s < kSrcGroup; ++s)
+                        if (s0 + s < P) raw[u][s] = ld_peer_i4(reinterpret_cast<const int4*>(p.bufs[s0 + s]) + v);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kDenseTile; ++u) {
+#pragma unroll
+                for (int s = 0; s < kSrcGroup; ++s)      // every rank computes bitwise the same sum
+                    if (s0 + s < P) {
+                        accs[u].x += __int_as_float(raw[u][s].x); accs[u].y += __int_as_float(raw[u][s].y);
+                        accs[u].z += __int_as_float(raw[u][s].z); accs[u].w += __int_as_float(raw[u][s].w);
+                    }
+            }
         }
-        acc.x *= scale; acc.y *= scale; acc.z *= scale; acc.w *= scale;
+#pragma unroll
+        for (int u = 0; u < kDenseTile; ++u) {
+            const int v = base + u * kDenseThreads + threadIdx.x;
+            if (v < hi) {
+                float4 acc = accs[u];
+                acc.x *= scale; acc.y *= scale; acc.z *= scale; acc.w *= scale;
 #pragma unroll 1
-        for (int t = 0; t < P; ++t) {
-            const int s = (rank + t) % P;
-            st_stream_f4(reinterpret_cast<float4*>(p.bufs[s]) + v, acc);
+                for (int t = 0; t < P; ++t) {
+                    const int s = (rank + t) % P;
+                    st_stream_f4(reinterpret_cast<float4*>(p.bufs[s]) + v, acc);
+                }
+            }
         }
     }
     // scalar tail (n % 4) is reduced by rank 0's CTA 0

@@ -29,7 +29,7 @@ __device__ __forceinline__ int region_of(const int* s_edges, int P, int i) {
     return d;
 }
 
-__global__ void __launch_bounds__(kThreads, 2) oktopk_fused_kernel(const OktParams p) {
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(const OktParams p) {
     __shared__ uint32_t s_hist[kHistBins];
     __shared__ int s_w[kWarps + 1];
     __shared__ int s_edges[OKT_MAXP + 1];
@@ -275,27 +275,51 @@ __global__ void __launch_bounds__(kThreads, 2) oktopk_fused_kernel(const OktPara
             if (p.residual_mode != RES_OKTOPK && pred) p.res[i] = 0.f;   // classic local error feedback
         };
 
-        const int n4r = (n4 + 31) / 32 * 32;      // keep warps converged through the ballots
-        for (int v = gtid; v < n4r; v += gthreads) {
-            const bool in = v < n4;
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (in) {
-                if (two_pass) {
-                    a = ld_stream_f4(r4 + v);
-                } else {
-                    a = ld_stream_f4(g4 + v);
-                    float4 r = ld_stream_f4(r4 + v);
-                    a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
-                    st_stream_f4(r4 + v, a);
+        // Streaming pass, kPackTile independent 128-bit vectors per thread per trip: all loads of a trip are
+        // issued before the first dependent instruction (bytes in flight per SM = 512 thr x 2 x 4 x 16 B = 64 KB),
+        // stores are write-through streaming, and the (rare: density ~ 1e-3) selections go through the
+        // warp-aggregated slot append.  16 B/element of HBM traffic, the roofline floor of the whole call.
+        const int trip = gridDim.x * kThreads * kPackTile;
+        for (int base = blockIdx.x * kThreads * kPackTile; base < n4; base += trip) {
+            float4 a[kPackTile];
+            float4 r[kPackTile];
+            bool in[kPackTile];
+#pragma unroll
+            for (int u = 0; u < kPackTile; ++u) {
+                const int v = base + u * kThreads + tid;
+                in[u] = v < n4;
+                a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                r[u] = a[u];
+                if (in[u]) {
+                    if (two_pass) {
+                        a[u] = ld_stream_f4(r4 + v);
+                    } else {
+                        a[u] = ld_stream_f4(g4 + v);
+                        r[u] = ld_stream_f4(r4 + v);
+                    }
                 }
-                st_stream_f4(g4 + v, make_float4(0.f, 0.f, 0.f, 0.f));
             }
-            const float m4 = fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w)));
-            if (__ballot_sync(0xffffffffu, in && m4 > thr_sel) == 0) continue;
-            emit(4 * v + 0, a.x, in);
-            emit(4 * v + 1, a.y, in);
-            emit(4 * v + 2, a.z, in);
-            emit(4 * v + 3, a.w, in);
+#pragma unroll
+            for (int u = 0; u < kPackTile; ++u) {
+                const int v = base + u * kThreads + tid;
+                if (in[u]) {
+                    if (!two_pass) {
+                        a[u].x += r[u].x; a[u].y += r[u].y; a[u].z += r[u].z; a[u].w += r[u].w;
+                        st_stream_f4(r4 + v, a[u]);
+                    }
+                    st_stream_f4(g4 + v, make_float4(0.f, 0.f, 0.f, 0.f));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kPackTile; ++u) {
+                const int v = base + u * kThreads + tid;
+                const float m4 = fmaxf(fmaxf(fabsf(a[u].x), fabsf(a[u].y)), fmaxf(fabsf(a[u].z), fabsf(a[u].w)));
+                if (__ballot_sync(0xffffffffu, in[u] && m4 > thr_sel) == 0) continue;
+                emit(4 * v + 0, a[u].x, in[u]);
+                emit(4 * v + 1, a[u].y, in[u]);
+                emit(4 * v + 2, a[u].z, in[u]);
+                emit(4 * v + 3, a[u].w, in[u]);
+            }
         }
         if (blockIdx.x == 0 && warp == 0 && (n & 3)) {
             int i = n4 * 4 + lane;
@@ -403,20 +427,55 @@ __global__ void __launch_bounds__(kThreads, 2) oktopk_fused_kernel(const OktPara
         float* gv = gat_val(me, p.L, par);
         const float fP = (float)P;
         int dropped = 0;
-        const int span = (hi - lo + 31) / 32 * 32;
-        for (int o = gtid; o < span; o += gthreads) {
-            const int i = lo + o;
-            const bool in = i < hi;
-            const float v = in ? __ldcg(p.g + i) : 0.f;
-            const bool nz = v != 0.f;
+        // one element: select, append to my gather slot, leave result/P (or 0) in place; converged per warp
+        auto visit = [&](int i, float v, bool in) -> float {
+            const bool nz = in && v != 0.f;
             const bool sel = (p.global_mode == GLB_THRESHOLD) ? (nz && fabsf(v) > gthr) : nz;
-            int pos = warp_append(&st->gather_cursor, sel);
+            const int pos = warp_append(&st->gather_cursor, sel);
             bool kept = false;
             if (sel) {
                 if (pos < gcap) { gi[pos] = i; gv[pos] = v; kept = true; }
                 else dropped++;
             }
-            if (nz) p.g[i] = (kept && p.global_mode != GLB_EXACT_TOPK) ? v / fP : 0.f;
+            return (kept && p.global_mode != GLB_EXACT_TOPK) ? v / fP : 0.f;
+        };
+        // scalar head / tail so that the body is 16-byte aligned (region edges are arbitrary)
+        const int first = min(hi, (lo + 3) & ~3), last = max(first, hi & ~3);
+        if (blockIdx.x == 0 && warp == 0) {
+            for (int part = 0; part < 2; ++part) {
+                const int b0 = part ? last : lo, b1 = part ? hi : first;
+                const int i = b0 + lane;
+                const bool in = i < b1;                       // at most 3 elements per part
+                const float v = in ? __ldcg(p.g + i) : 0.f;
+                const float o = visit(i, v, in);
+                if (in && v != 0.f) p.g[i] = o;
+            }
+        }
+        const int nv = (last - first) >> 2;
+        const float4* gv4 = reinterpret_cast<const float4*>(p.g + first);
+        const int nvr = (nv + 31) / 32 * 32;
+        for (int q0 = blockIdx.x * kThreads * kScanTile; q0 < nvr; q0 += gridDim.x * kThreads * kScanTile) {
+            float4 a[kScanTile];
+            bool in[kScanTile];
+#pragma unroll
+            for (int u = 0; u < kScanTile; ++u) {
+                const int q = q0 + u * kThreads + tid;
+                in[u] = q < nv;
+                a[u] = in[u] ? __ldcg(gv4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < kScanTile; ++u) {
+                const int q = q0 + u * kThreads + tid;
+                const bool any = in[u] && (a[u].x != 0.f || a[u].y != 0.f || a[u].z != 0.f || a[u].w != 0.f);
+                if (__ballot_sync(0xffffffffu, any) == 0) continue;
+                const int i = first + 4 * q;
+                float4 o;
+                o.x = visit(i + 0, a[u].x, in[u]);
+                o.y = visit(i + 1, a[u].y, in[u]);
+                o.z = visit(i + 2, a[u].z, in[u]);
+                o.w = visit(i + 3, a[u].w, in[u]);
+                if (any) *reinterpret_cast<float4*>(p.g + i) = o;
+            }
         }
         int dsum = warp_sum(dropped);
         if (lane == 0 && dsum) atomicAdd(&st->stat_overflow_gather, dsum);
@@ -506,7 +565,7 @@ int okt_max_coop_grid(int device) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, oktopk_fused_kernel, kThreads, 0);
     if (per < 1) per = 1;
-    if (per > 2) per = 2;
+    if (per > kCtasPerSm) per = kCtasPerSm;
     return sms * per;
 }
 

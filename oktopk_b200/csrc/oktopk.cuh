@@ -17,6 +17,9 @@ constexpr int kChunk = 1024;              // (idx,val) entries per pulled chunk 
 constexpr int kHistBins = 2048;           // 11-bit radix digit
 constexpr int kMaxWarpsTotal = 16384;     // per-warp counters for the quantile cuts
 constexpr int kGuardMax = 8;
+constexpr int kCtasPerSm = 1;           // persistent kernels: one 512-thread CTA per SM (<= 128 registers/thread)
+constexpr int kPackTile = 4;            // 128-bit vectors per thread per trip of the streaming pass
+constexpr int kScanTile = 4;            // same for the region scan of the global selection
 
 // ---- device-resident, zero-initialised, one per bucket ---------------------------------------
 struct OktState {

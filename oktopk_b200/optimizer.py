@@ -82,12 +82,13 @@ class _BucketedComm:
         # device-resident learning rates (one float per param group): the fused update kernels read lr from
         # memory so that a captured CUDA graph of the whole step stays valid when the schedule moves
         self._lr_dev = None
-        self._lr_pin, self._lr_ring, self._lr_last = [], 0, None
+        self._lr_pin, self._lr_ev, self._lr_ring, self._lr_last = [], [], 0, None
         dev0 = self._buckets[0].params[0].device if self._buckets else torch.device("cpu")
         if dev0.type == "cuda" and ext.available():
             G = len(self.param_groups)
             self._lr_dev = torch.zeros(max(G, 1), dtype=torch.float32, device=dev0)
-            self._lr_pin = [torch.zeros(max(G, 1), dtype=torch.float32).pin_memory() for _ in range(4)]
+            self._lr_pin = [torch.zeros(max(G, 1), dtype=torch.float32).pin_memory() for _ in range(8)]
+            self._lr_ev = [None] * len(self._lr_pin)
 
     def _group_lr(self, gi: int) -> float:
         return float(self.param_groups[gi]["lr"])
@@ -102,9 +103,14 @@ class _BucketedComm:
             return
         self._lr_ring = (self._lr_ring + 1) % len(self._lr_pin)
         pin = self._lr_pin[self._lr_ring]
+        if self._lr_ev[self._lr_ring] is not None:          # the host may run many (graph-replayed) steps ahead:
+            self._lr_ev[self._lr_ring].synchronize()        # never overwrite a staging slot whose copy is pending
         for i, v in enumerate(vals):
             pin[i] = v
         self._lr_dev.copy_(pin, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._lr_ev[self._lr_ring] = ev
         self._lr_last = vals
 
     def _lr_ptr(self, gi: int) -> int:

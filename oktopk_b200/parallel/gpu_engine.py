@@ -37,7 +37,7 @@ def _round_up(x: int, m: int) -> int:
 
 class CudaBucketEngine:
     def __init__(self, numel: int, cfg: OkTopkConfig, world: World, name: str = "bucket",
-                 max_density: Optional[float] = None, dense_grid: int = 64):
+                 max_density: Optional[float] = None, dense_grid: int = 0):
         self.C = ext.require()
         C = self.C
         self.cfg = cfg
@@ -67,7 +67,8 @@ class CudaBucketEngine:
         self.grid = C.max_coop_grid(self.device.index)
         if cfg.comm_ctas > 0:
             self.grid = min(self.grid, cfg.comm_ctas)
-        self.dense_grid = dense_grid
+        # dense two-shot kernel: one CTA per SM (its per-CTA cross-GPU barrier needs same-index CTAs co-scheduled)
+        self.dense_grid = dense_grid or torch.cuda.get_device_properties(self.device).multi_processor_count
         # ---- one symmetric allocation: [grad | comm block | dense flags] -------------------
         self.grad_bytes = _round_up(self.n * 4, 4096)
         self.comm_off = self.grad_bytes

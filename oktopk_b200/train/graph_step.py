@@ -37,7 +37,7 @@ class GraphedTrainStep:
 
     def _key(self) -> Tuple:
         cfg = self.opt._cfg
-        key = []
+        key = [("density", self.opt.get_current_density())]     # k and the guard limits are baked into the launch
         for eng in self._engines():
             if eng is None:
                 return ("nograph",)
@@ -73,7 +73,7 @@ class GraphedTrainStep:
             self.eager_left -= 1
             return self._eager(batch)
         key = self._key()
-        if key == ("nograph",) or any(any(f is True for f in k) for k in key):
+        if key == ("nograph",) or any(any(f is True for f in k) for k in key[1:]):
             # rare flavours (exact-threshold / re-partition iterations, 1 in 32..128) stay eager: capturing them
             # costs more than they save, and the common flavour is what the step time is made of
             return self._eager(batch)
