@@ -86,6 +86,7 @@ static py::dict read_state(uint64_t st, int P, uint64_t stream) {
     d["local_count"] = s->stat_local_count; d["global_count"] = s->stat_global_count;
     d["recv_total"] = s->stat_recv_total; d["gather_total"] = s->stat_gather_total;
     d["overflow_send"] = s->stat_overflow_send; d["overflow_gather"] = s->stat_overflow_gather;
+    d["fault"] = s->fault;
     return d;
 }
 
@@ -139,6 +140,7 @@ static void oktopk_run(uint64_t g, uint64_t res, uint64_t st, const std::vector<
     p.l_factor = (float)getf("l_factor", 1.012);
     p.g_low_cnt = getf("g_low_cnt", 0.0); p.g_high_cnt = getf("g_high_cnt", 1e30);
     p.g_inc = (float)getf("g_inc", 1.008); p.g_dec = (float)getf("g_dec", 1.008);
+    p.timeout_ns = (unsigned long long)(getf("timeout_s", 0.0) * 1e9);
     if (geti("split_phases", 0)) {
         // ablation / debugging: one launch per phase instead of the single persistent kernel
         for (int ph = p.phase_begin; ph < p.phase_end; ++ph) {
@@ -166,17 +168,20 @@ static void gather_run(uint64_t g, uint64_t res, uint64_t st, const std::vector<
     p.gauss_factor = o.contains("gauss_factor") ? (float)o["gauss_factor"].cast<double>() : 1.02f;
     p.density = (float)o["density"].cast<double>();
     p.pull_tma = o.contains("pull_tma") ? o["pull_tma"].cast<int>() : 1;
+    p.timeout_ns = o.contains("timeout_s") ? (unsigned long long)(o["timeout_s"].cast<double>() * 1e9) : 0ULL;
     ck(launch_gather_scheme(p, grid, S_(stream)), "gather scheme launch");
 }
 
 static void dense_run(const std::vector<uint64_t>& bufs, const std::vector<uint64_t>& flags, uint64_t epoch, int n,
-                      int rank, int grid, uint64_t stream) {
+                      int rank, int grid, uint64_t stream, uint64_t st, double timeout_s) {
     DenseParams p;
     std::memset(&p, 0, sizeof(p));
     if (bufs.size() > OKT_MAXP || bufs.size() != flags.size()) throw std::runtime_error("bad peer tables");
     for (size_t i = 0; i < bufs.size(); ++i) { p.bufs[i] = P_<float>(bufs[i]); p.flags[i] = P_<uint64_t>(flags[i]); }
     p.epoch = P_<unsigned long long>(epoch);
     p.n = n; p.P = (int)bufs.size(); p.rank = rank; p.scale = 1.0f / (float)p.P;
+    p.fault = st ? &P_<OktState>(st)->fault : nullptr;
+    p.timeout_ns = (unsigned long long)(timeout_s * 1e9);
     ck(launch_dense_allreduce(p, grid, S_(stream)), "dense allreduce launch");
 }
 
@@ -221,7 +226,11 @@ PYBIND11_MODULE(_C, m) {
     m.def("max_coop_grid", &okt_max_coop_grid);
     m.def("oktopk_run", &oktopk_run);
     m.def("gather_run", &gather_run);
-    m.def("dense_run", &dense_run);
+    m.def("dense_run", &dense_run, py::arg("bufs"), py::arg("flags"), py::arg("epoch"), py::arg("n"), py::arg("rank"),
+          py::arg("grid"), py::arg("stream"), py::arg("st") = 0, py::arg("timeout_s") = 0.0);
+    m.def("clear_fault", [](uint64_t st, uint64_t stream) {
+        ck(cudaMemsetAsync(&P_<OktState>(st)->fault, 0, sizeof(int), S_(stream)), "clear_fault");
+    });
     m.def("kth_abs", &kth_abs);
     m.def("fused_sgd", &fused_sgd, py::arg("p"), py::arg("g"), py::arg("mom"), py::arg("n"), py::arg("lr"),
           py::arg("momentum"), py::arg("dampening"), py::arg("wd"), py::arg("nesterov"), py::arg("first"),

@@ -54,11 +54,39 @@ __device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned 
 __device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
-// Spin until the mailbox word carries `epoch` in its high half; returns the low half (payload).
-__device__ __forceinline__ uint32_t wait_mailbox(const uint64_t* box, uint32_t epoch) {
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Failure detection on the device: every cross-GPU spin is bounded.  When a peer does not show up within
+// `timeout_ns` the waiter records a fault code in *fault (device memory, read lazily by the host) and gives up,
+// so a dead or wedged peer turns into a reported error instead of a hung GPU.  Once a fault is recorded every
+// later wait of the same bucket returns immediately.
+enum FaultCode : int { FAULT_NONE = 0, FAULT_RS_TIMEOUT = 1, FAULT_AG_TIMEOUT = 2, FAULT_CUT_TIMEOUT = 3, FAULT_DENSE_TIMEOUT = 4 };
+
+struct SpinGuard {
+    int* fault;
+    unsigned long long timeout_ns;
+    int code;
+};
+
+// Spin until the mailbox word carries `epoch` in its high half; returns the low half (payload), 0 on fault.
+__device__ __forceinline__ uint32_t wait_mailbox(const uint64_t* box, uint32_t epoch, const SpinGuard& sg) {
     uint64_t v = ld_acquire_sys_u64(box);
+    if ((uint32_t)(v >> 32) == epoch) return (uint32_t)v;
+    const unsigned long long t0 = globaltimer_ns();
+    uint32_t spins = 0;
     while ((uint32_t)(v >> 32) != epoch) {
         __nanosleep(20);
+        if ((++spins & 1023u) == 0 && sg.fault != nullptr) {
+            if (*reinterpret_cast<volatile int*>(sg.fault) != FAULT_NONE) return 0u;
+            if (sg.timeout_ns != 0ULL && globaltimer_ns() - t0 > sg.timeout_ns) {
+                atomicCAS(sg.fault, FAULT_NONE, sg.code);
+                return 0u;
+            }
+        }
         v = ld_acquire_sys_u64(box);
     }
     return (uint32_t)v;

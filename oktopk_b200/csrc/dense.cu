@@ -26,7 +26,15 @@ __device__ __forceinline__ void cta_peer_barrier(const DenseParams& p, int phase
         fence_acq_rel_sys();
         st_release_sys_u64(p.flags[tid] + slot + p.rank, ticket);        // tell peer `tid` I am here
         const uint64_t* mine = p.flags[p.rank] + slot + tid;             // wait for peer `tid`
-        while (ld_acquire_sys_u64(mine) < ticket) { __nanosleep(20); }
+        const unsigned long long t0 = globaltimer_ns();
+        uint32_t spins = 0;
+        while (ld_acquire_sys_u64(mine) < ticket) {
+            __nanosleep(20);
+            if ((++spins & 1023u) == 0 && p.fault != nullptr) {
+                if (*reinterpret_cast<volatile int*>(p.fault) != FAULT_NONE) break;
+                if (p.timeout_ns != 0ULL && globaltimer_ns() - t0 > p.timeout_ns) { atomicCAS(p.fault, FAULT_NONE, FAULT_DENSE_TIMEOUT); break; }
+            }
+        }
     }
     __syncthreads();
 }

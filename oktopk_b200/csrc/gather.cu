@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(kThreads, 2) gather_scheme_kernel(const Gather
         __syncthreads();
         if (tid == 0) st->gather_cursor = 0;
     }
-    if (tid < P) s_cnt[tid] = (int)wait_mailbox(ag_mbox(me, p.L, par, tid), epoch);
+    if (tid < P) s_cnt[tid] = (int)wait_mailbox(ag_mbox(me, p.L, par, tid), epoch, SpinGuard{&st->fault, p.timeout_ns, FAULT_AG_TIMEOUT});
     __syncthreads();
     {
         int T = 0;

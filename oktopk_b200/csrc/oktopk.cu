@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
                     for (int j = 0; j < P - 1; ++j) st_relaxed_sys_u32(reinterpret_cast<uint32_t*>(dst + j), (uint32_t)st->cuts[j]);
                     st_release_sys_u64(cut_mbox(p.peers[tid], p.L, par, rank), make_mail(epoch, 1u));
                 }
-                if (tid < P) wait_mailbox(cut_mbox(me, p.L, par, tid), epoch);
+                if (tid < P) wait_mailbox(cut_mbox(me, p.L, par, tid), epoch, SpinGuard{&st->fault, p.timeout_ns, FAULT_CUT_TIMEOUT});
                 __syncthreads();
                 if (tid < P - 1) {
                     long long sum = 0;
@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
     // ======================================================================== PH_REDUCE
     if (p.phase_begin <= PH_REDUCE && PH_REDUCE < p.phase_end) {
         if (tid < P) {
-            s_cnt[tid] = (int)wait_mailbox(rs_mbox(me, p.L, par, tid), epoch);
+            s_cnt[tid] = (int)wait_mailbox(rs_mbox(me, p.L, par, tid), epoch, SpinGuard{&st->fault, p.timeout_ns, FAULT_RS_TIMEOUT});
             s_thr[tid] = __uint_as_float(ld_relaxed_sys_u32(reinterpret_cast<uint32_t*>(rs_thr(me, p.L, par, tid))));
         }
         __syncthreads();
@@ -493,7 +493,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
 
     // ======================================================================== PH_FINAL
     if (p.phase_begin <= PH_FINAL && PH_FINAL < p.phase_end) {
-        if (tid < P) s_cnt[tid] = (int)wait_mailbox(ag_mbox(me, p.L, par, tid), epoch);
+        if (tid < P) s_cnt[tid] = (int)wait_mailbox(ag_mbox(me, p.L, par, tid), epoch, SpinGuard{&st->fault, p.timeout_ns, FAULT_AG_TIMEOUT});
         __syncthreads();
         int T = 0;
         for (int s = 0; s < P; ++s) T += s_cnt[s];

@@ -43,7 +43,7 @@ struct OktState {
     int stat_overflow_send;               // cumulative drops because a slot was full
     int stat_overflow_gather;
     int stat_mode;
-    int pad0;
+    int fault;                            // FaultCode of the first bounded wait that timed out (0 = healthy)
     double gs_sum, gs_sumsq;              // Gaussiank moments
     uint32_t hist[kHistBins];
     int wcounts[kMaxWarpsTotal];
@@ -116,6 +116,7 @@ struct OktParams {
     float l_factor;
     double g_low_cnt, g_high_cnt;
     float g_inc, g_dec;
+    unsigned long long timeout_ns;      // bound of every cross-GPU wait (0 = unbounded)
 };
 
 // ---- gather-type schemes (TopkAopt / Gaussiank / TopkA): select -> own slot -> everyone adds all ---
@@ -135,6 +136,7 @@ struct GatherParams {
     float gauss_factor;
     float density;
     int pull_tma;
+    unsigned long long timeout_ns;
 };
 
 // ---- dense allreduce over peer memory -------------------------------------------------------------
@@ -144,6 +146,8 @@ struct DenseParams {
     unsigned long long* epoch;  // local, one counter per CTA
     int n, P, rank;
     float scale;              // 1/P
+    int* fault;               // bucket fault word (OktState::fault)
+    unsigned long long timeout_ns;
 };
 
 // ---- host-callable launchers (implemented in the .cu files) ----------------------------------------

@@ -207,6 +207,10 @@ class _BucketedComm:
     def comm_stats(self) -> Dict:
         return self._allreducer.stats()
 
+    def check_faults(self) -> None:
+        """Raise / call ``err_handler`` if a peer timed out inside a communication kernel (synchronous read)."""
+        self._allreducer.check_faults()
+
     def close(self) -> None:
         for h in self._hook_handles:
             h.remove()

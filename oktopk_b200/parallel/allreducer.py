@@ -121,6 +121,20 @@ class AllReducer:
                        "edges": st.region_offsets + [st.numel]}
         return out if name is None else out[name]
 
+    def check_faults(self) -> None:
+        """Failure detection: surfaces device-side peer timeouts.  If an ``err_callback`` was given
+        (``DistributedOptimizer(err_handler=...)``) it is invoked as ``cb(new_num_workers, new_rank)`` with the
+        current world (the caller decides how to shrink); otherwise ``PeerTimeoutError`` propagates."""
+        for eng in self._engines.values():
+            try:
+                eng.check_fault()
+            except RuntimeError:
+                if self.err_callback is not None:
+                    self.err_callback(self.world.size, self.world.rank)
+                    eng.clear_fault()
+                else:
+                    raise
+
     def state_dict(self) -> Dict:
         sd = {"train_epoch": self.train_epoch, "buckets": {}}
         for nm, eng in self._engines.items():

@@ -35,6 +35,10 @@ def _round_up(x: int, m: int) -> int:
     return (int(x) + m - 1) // m * m
 
 
+class PeerTimeoutError(RuntimeError):
+    """A rank of the peer group did not reach a handshake in time (device-side failure detection)."""
+
+
 class CudaBucketEngine:
     def __init__(self, numel: int, cfg: OkTopkConfig, world: World, name: str = "bucket",
                  max_density: Optional[float] = None, dense_grid: int = 0):
@@ -131,14 +135,14 @@ class CudaBucketEngine:
         if self.P == 1:
             return
         self.C.dense_run(self.peer_grad, self.peer_flags, self.dense_epoch_ptr, self.n, self.rank,
-                         self.dense_grid, s)
+                         self.dense_grid, s, self.state_ptr, float(self.cfg.peer_timeout_s))
 
     def _fused(self, compressor: str, density: Optional[float], s: int, g: torch.Tensor) -> None:
         cfg = self.cfg
         k = self.k_now(density)
         it = self.host.counter - cfg.warmup_iters
         o: Dict = {"pull_tma": 1 if cfg.pull_mode == "tma" else 0, "deterministic": int(cfg.deterministic),
-                   "split_phases": 0 if cfg.fused else 1}
+                   "split_phases": 0 if cfg.fused else 1, "timeout_s": float(cfg.peer_timeout_s)}
         if compressor == "oktopk":
             o.update(
                 exact_local=int(it % cfg.local_recompute_interval == 0),
@@ -165,7 +169,7 @@ class CudaBucketEngine:
         d = cfg.density if density is None else density
         k = self.k_now(density)
         it = self.host.counter - cfg.warmup_iters
-        o: Dict = {"density": d, "pull_tma": 1 if cfg.pull_mode == "tma" else 0}
+        o: Dict = {"density": d, "pull_tma": 1 if cfg.pull_mode == "tma" else 0, "timeout_s": float(cfg.peer_timeout_s)}
         if compressor == "topkA":
             o["select_mode"] = GS_EXACT_TOPK
         elif compressor == "topkAopt":
@@ -199,6 +203,17 @@ class CudaBucketEngine:
         # scalars moved by this rank in the last call (idx + val per entry), cf. the 6k(P-1)/P bound
         d["volume_elems"] = 2 * (d["recv_total"] + d["gather_total"])
         return d
+
+    def check_fault(self) -> None:
+        """Raise if a bounded cross-GPU wait timed out inside a kernel (a peer died or wedged).  Synchronous."""
+        code = int(self.stats().get("fault", 0))
+        if code:
+            names = {1: "reduce-scatter mailbox", 2: "allgather mailbox", 3: "region-cut mailbox", 4: "dense barrier"}
+            raise PeerTimeoutError("bucket %s: peer wait timed out in the %s (fault %d, timeout %.1fs)"
+                                   % (self.name, names.get(code, "?"), code, self.cfg.peer_timeout_s))
+
+    def clear_fault(self) -> None:
+        self.C.clear_fault(self.state_ptr, torch.cuda.current_stream().cuda_stream)
 
     def state_dict(self) -> Dict:
         d = self.stats()

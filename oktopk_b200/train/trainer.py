@@ -316,6 +316,7 @@ def robust_ssgd(dnn: str, dataset: Optional[str], data_dir: Optional[str], nwork
             done += 1
             if done % log_every == 0:
                 loss = tr.last_loss()
+                tr.optimizer.check_faults()
                 dt = (time.perf_counter() - t_last) / log_every
                 t_last = time.perf_counter()
                 if w.rank == 0:

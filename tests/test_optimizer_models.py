@@ -329,3 +329,27 @@ def test_robust_ssgd_driver_runs(tmp_path):
                      max_iters=3, log_every=1, checkpoint_dir=str(tmp_path), device=torch.device("cpu"))
     assert tr.train_iter == 3
     assert any(f.endswith(".pth") for f in os.listdir(tmp_path))
+
+
+def test_signal_handler_saves_interrupted_state_and_resumes(tmp_path):
+    """the reference defines SLURM signal handlers but never installs them; here they are live."""
+    import signal
+    from oktopk_b200.train.trainer import Trainer
+    from oktopk_b200.utils import elastic
+    tr = Trainer(dnn="mnistnet", dataset="mnist", batch_size=4, lr=0.05, compressor="oktopk", density=0.05,
+                 device=torch.device("cpu"))
+    tr.train_step()
+    hit = []
+    prev = elastic.install_signal_handlers(tr, str(tmp_path), exit_after=False, on_signal=hit.append)
+    try:
+        os.kill(os.getpid(), signal.SIGUSR1)
+        assert hit == [signal.SIGUSR1] and os.path.exists(elastic.interrupted_path(str(tmp_path), 0))
+        tr.train_step()
+        assert elastic.resume_if_interrupted(tr, str(tmp_path)) and tr.train_iter == 1
+        assert not elastic.resume_if_interrupted(tr, str(tmp_path))
+        tr.optimizer.check_faults()                       # healthy: no-op
+        elastic.shrink_world(tr, 1, 0)
+    finally:
+        for s, h in prev.items():
+            signal.signal(s, h)
+        tr.close()
