@@ -121,7 +121,7 @@ class BertPreTrainingHeads(nn.Module):
         self.transform = nn.Linear(c.hidden_size, c.hidden_size)
         self.transform_norm = nn.LayerNorm(c.hidden_size, eps=c.layer_norm_eps)
         self.act = _act(c.hidden_act)
-        self.decoder_weight = nn.Parameter(torch.empty(c.vocab_size, c.hidden_size))
+        self.decoder_weight = nn.Parameter(torch.empty(c.vocab_size, c.hidden_size).normal_(std=c.initializer_range))
         self.decoder_bias = nn.Parameter(torch.zeros(c.vocab_size))
         self.seq_relationship = nn.Linear(c.hidden_size, 2)
 

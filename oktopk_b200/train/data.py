@@ -129,6 +129,17 @@ def build_dataset(name: str, data_dir: Optional[str] = None, train: bool = True,
     if name == "ptb":
         return SyntheticPTB(seed=seed, **{k: v for k, v in kw.items() if k in ("batch_size", "num_steps")})
     if name in ("wikipedia", "bert"):
+        if data_dir:
+            # a real corpus on disk: <data_dir>/{train,valid}.txt (or corpus.txt) + optional vocab.txt
+            import os
+            from ..utils.tokenization import BertTokenizer
+            from .bert_data import BERTDataset
+            for cand in (("train.txt" if train else "valid.txt"), "corpus.txt"):
+                path = os.path.join(data_dir, cand)
+                if os.path.isfile(path):
+                    vf = os.path.join(data_dir, "vocab.txt")
+                    tok = BertTokenizer(vf) if os.path.isfile(vf) else BertTokenizer.synthetic()
+                    return BERTDataset(path, tok, seq_len=kw.get("seq", 128), seed=seed)
         return SyntheticWikipedia(seq=kw.get("seq", 128), seed=seed)
     raise ValueError("unknown dataset %r" % name)
 
