@@ -43,7 +43,14 @@ def create_net(num_classes: int, dnn: str = "resnet20", **kwargs):
     elif d == "lstm":
         net = PTBLSTM(vocab_size=kwargs.get("vocab_size", 10000), batch_size=kwargs.get("batch_size", 20))
     elif d in ("bert", "bert_base"):
-        net = bert_base(kwargs.get("depth", 4))
+        cfg = kwargs.get("config")
+        if isinstance(cfg, str):
+            cfg = BertConfig.from_json_file(cfg)
+        cfg = cfg or BertConfig.bert_base()
+        if kwargs.get("num_hidden_layers"):
+            import dataclasses
+            cfg = dataclasses.replace(cfg, num_hidden_layers=int(kwargs["num_hidden_layers"]))
+        net = BertForPreTraining(cfg, kwargs.get("depth", 4), recompute=bool(kwargs.get("recompute", False)))
     else:
         raise ValueError("unknown dnn %r (have %s)" % (dnn, DNNS))
     return net, ext

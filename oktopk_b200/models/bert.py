@@ -196,9 +196,10 @@ class PretrainingCriterion(nn.Module):
 
 
 class BertForPreTraining(nn.Module):
-    def __init__(self, config: Optional[BertConfig] = None, depth: int = 4):
+    def __init__(self, config: Optional[BertConfig] = None, depth: int = 4, recompute: bool = False):
         super().__init__()
         self.config = config or BertConfig()
+        self.recompute = recompute           # ``--recompute_step`` (BERT/runtime.py:546-557, modeling.py:414-431)
         self.stages = nn.ModuleList(build_stages(self.config, depth))
         self.criterion = PretrainingCriterion(self.config.vocab_size)
         self.apply(self._init)
@@ -220,7 +221,11 @@ class BertForPreTraining(nn.Module):
         mask = None if attention_mask is None else extended_attention_mask(attention_mask)
         x = self.stages[0](input_ids, token_type_ids, mask)
         for st in self.stages[1:-1]:
-            x = st(x, mask)
+            if self.recompute and self.training:
+                from torch.utils.checkpoint import checkpoint
+                x = checkpoint(st, x, mask, use_reentrant=False)
+            else:
+                x = st(x, mask)
         scores, nsp = self.stages[-1](x, mask)
         if masked_lm_labels is not None and next_sentence_label is not None:
             return self.criterion(scores, nsp, masked_lm_labels, next_sentence_label)

@@ -51,6 +51,16 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--no-fused", action="store_true", help="phase-per-launch ablation of the persistent kernel")
     p.add_argument("--deterministic", action="store_true")
     p.add_argument("--seed", type=int, default=0)
+    p.add_argument("--cuda-graph", action="store_true", help="capture forward+backward+allreduce+update into CUDA graphs")
+    p.add_argument("--fp16", action="store_true", help="fp16 autocast (reference: apex amp O3, main_bert.py:1009-1023)")
+    p.add_argument("--bf16", action="store_true", help="bf16 autocast")
+    p.add_argument("--recompute_step", action="store_true", help="activation recomputation in the BERT encoder")
+    p.add_argument("--dataparallel", action="store_true", help="accepted for parity: data parallelism is the only mode")
+    p.add_argument("--do_train", action="store_true", help="accepted for parity")
+    p.add_argument("--do_lower_case", action="store_true", help="accepted for parity")
+    p.add_argument("--train_path", type=str, default=None, help="BERT corpus (one sentence per line); implies --data-dir")
+    p.add_argument("--vocab_path", type=str, default=None)
+    p.add_argument("--bert_config_path", type=str, default=None)
     return p
 
 
@@ -60,10 +70,20 @@ def main(argv=None) -> int:
     from .trainer import preset_for, robust_ssgd
     okt.init()
     dnn = args.dnn
-    if args.module:                       # 'models.bert12.depth=4'
+    model_kwargs = {}
+    if args.module:                       # 'models.bert12.depth=4' => 12 layers run as 4 stage modules
         m = re.search(r"bert(\d+)\.depth=(\d+)", args.module)
         if m:
             dnn = "bert_base"
+            model_kwargs.update(num_hidden_layers=int(m.group(1)), depth=int(m.group(2)))
+    cfg_path = args.bert_config_path or (args.config_path if args.config_path and args.config_path.endswith(".json")
+                                         and os.path.isfile(args.config_path) and "bert_config" in args.config_path else None)
+    if cfg_path:
+        model_kwargs["config"] = cfg_path
+    if args.recompute_step:
+        model_kwargs["recompute"] = True
+    if args.train_path and not args.data_dir:
+        args.data_dir = os.path.dirname(os.path.abspath(args.train_path))
     cfg = okt.preset(args.preset or preset_for(dnn), density=args.density, sigma_scale=args.sigma_scale)
     over = {}
     if args.warmup_iters is not None:
@@ -79,7 +99,9 @@ def main(argv=None) -> int:
                      args.max_epochs, compression=args.compression, compressor=args.compressor,
                      nwpernode=args.nwpernode, sigma_scale=args.sigma_scale, pretrain=args.pretrain,
                      density=args.density, max_iters=args.max_iters, checkpoint_dir=args.checkpoint_dir, cfg=cfg,
-                     log_dir=args.log_dir, seq_len=args.max_seq_length, seed=args.seed, backend=args.backend)
+                     log_dir=args.log_dir, seq_len=args.max_seq_length, seed=args.seed, backend=args.backend,
+                     cuda_graph=args.cuda_graph, model_kwargs=model_kwargs or None,
+                     autocast="bf16" if args.bf16 else ("fp16" if args.fp16 else None))
     if okt.rank() == 0:
         print("final loss %.5f after %d iterations" % (tr.last_loss(), tr.train_iter))
     tr.close()

@@ -48,7 +48,8 @@ class Trainer:
                  cfg: Optional[OkTopkConfig] = None, world: Optional[World] = None, device: Optional[torch.device] = None,
                  seed: int = 0, prefix: str = "run", log_dir: Optional[str] = None, num_workers: int = 0,
                  seq_len: int = 128, t_total: int = -1, warmup: float = -1, pretrain: Optional[str] = None,
-                 norm_clip: Optional[float] = None, backend: Optional[str] = None, cuda_graph: bool = False):
+                 norm_clip: Optional[float] = None, backend: Optional[str] = None, cuda_graph: bool = False,
+                 model_kwargs: Optional[dict] = None, autocast: Optional[str] = None):
         self.world = world or _world()
         self.rank, self.nworkers = self.world.rank, self.world.size
         self.dnn = dnn
@@ -63,7 +64,9 @@ class Trainer:
         self.seq_len = seq_len
         # ---- model ------------------------------------------------------------------------
         self.num_classes = D.DATASET_CLASSES.get(self.dataset, 10)
-        net, self.ext = create_net(self.num_classes, dnn)
+        net, self.ext = create_net(self.num_classes, dnn, **(model_kwargs or {}))
+        # optional mixed precision (the reference's --fp16 is apex O3, off in every script; bf16 autocast here)
+        self.autocast = {"bf16": torch.bfloat16, "fp16": torch.float16}.get(autocast or "", None)
         self.net = net.to(self.device)
         self.is_bert = dnn.startswith("bert")
         if pretrain:
@@ -144,6 +147,12 @@ class Trainer:
 
     # ------------------------------------------------------------------ one micro-step: forward + backward
     def _forward_loss(self, batch):
+        if self.autocast is not None:
+            with torch.autocast(self.device.type, dtype=self.autocast):
+                return self._forward_loss_impl(batch)
+        return self._forward_loss_impl(batch)
+
+    def _forward_loss_impl(self, batch):
         if self.is_bert:
             ids, seg, mask, labels, nxt = batch
             return self.net(ids, seg, mask, labels, nxt), None
