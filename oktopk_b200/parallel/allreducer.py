@@ -49,6 +49,7 @@ class AllReducer:
         self._engines: Dict[str, "object"] = {}
         self._timers: Dict[str, list] = {}
         self._running = True
+        self.profile_records: list = []              # filled when settings.PROFILING_NORM is on
 
     # ------------------------------------------------------------------ density schedule
     def get_current_density(self) -> float:
@@ -81,6 +82,9 @@ class AllReducer:
 
     def reduce_bucket(self, name: str, flat: torch.Tensor, stream=None) -> torch.Tensor:
         density = self.get_current_density()
+        from ..utils import settings
+        if settings.PROFILING_NORM and self.cfg.sparse:
+            return self._reduce_profiled(name, flat, stream, density)
         if name in self._engines:
             return self._engines[name].reduce(self.compressor.name, density, stream=stream, g=flat)
         st = self._dist_states.get(name)
@@ -89,6 +93,38 @@ class AllReducer:
         t0 = time.perf_counter()
         out = algorithms.sparse_allreduce(self.compressor.name, flat, st, self.cfg, self.world, density)
         self._timers.setdefault(name, []).append(time.perf_counter() - t0)
+        return out
+
+    def _reduce_profiled(self, name: str, flat: torch.Tensor, stream, density: float) -> torch.Tensor:
+        """``settings.PROFILING_NORM`` (``VGG/allreducer.py:584-606,1072-1080``): one extra dense allreduce of the
+        error-compensated gradient per step gives the true global top-k, against which the sparse result's relative
+        error (the paper's xi) and the selected counts are recorded.  Diagnostic mode: synchronous and slow."""
+        from ..utils.metrics import sparsification_error
+        eng = self._engines.get(name)
+        st = self._dist_states.get(name)
+        res = eng.residual if eng is not None else (st.residual if st is not None else None)
+        with torch.no_grad():
+            acc = flat.detach().clone()
+            if res is not None and res.numel() == acc.numel():
+                acc += res
+            if self.world.size > 1:
+                self.world.all_reduce_sum(acc)
+            acc /= self.world.size
+        if eng is not None:
+            out = eng.reduce(self.compressor.name, density, stream=stream, g=flat)
+            if flat.is_cuda:
+                torch.cuda.synchronize()
+        else:
+            if st is None:
+                st = self._dist_states[name] = SparseState(flat.numel(), self.world.size)
+            out = algorithms.sparse_allreduce(self.compressor.name, flat, st, self.cfg, self.world, density)
+        k = max(int(flat.numel() * density), 1)
+        rec = sparsification_error(acc, out, k)
+        rec["bucket"], rec["density"] = name, density
+        self.profile_records.append(rec)
+        if self.writer is not None and hasattr(self.writer, "add_scalars"):
+            self.writer.add_scalars("profiling_norm/" + name, {k2: v for k2, v in rec.items() if isinstance(v, (int, float))},
+                                    len(self.profile_records))
         return out
 
     # ------------------------------------------------------------------ functional form

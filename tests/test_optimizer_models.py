@@ -353,3 +353,17 @@ def test_signal_handler_saves_interrupted_state_and_resumes(tmp_path):
         for s, h in prev.items():
             signal.signal(s, h)
         tr.close()
+
+
+def test_profiling_norm_records_sparsification_error(monkeypatch):
+    """``settings.PROFILING_NORM``: relative error of the sparse result vs the true dense top-k (the paper's xi)."""
+    from oktopk_b200.utils import settings
+    monkeypatch.setattr(settings, "PROFILING_NORM", True)
+    ar = okt.AllReducer("oktopk", True, 0.01)
+    g = torch.randn(20_000)
+    ar.run(g.clone())
+    ar.run(torch.randn(20_000))
+    assert len(ar.profile_records) == 2
+    r = ar.profile_records[0]
+    # P=1 exact iteration: the result is the strict top-k => only the k-th element is missing from the ideal set
+    assert 0.0 <= r["eps"] < 0.05 and r["nnz"] == 199 and r["grad_norm"] > 0
