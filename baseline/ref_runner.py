@@ -77,9 +77,13 @@ def run_reference(args, MODELS) -> dict:
         net = models.VGG("VGG16").to(dev)
         criterion = torch.nn.CrossEntropyLoss().to(dev)
 
+        _tw = torch.randn(3 * 32 * 32, 10, generator=torch.Generator().manual_seed(4242))
+
         def make_batch(i):
+            # same synthetic task as the other arm: N(0,1) images, labels = argmax of a fixed random linear map
             g = torch.Generator().manual_seed(1234 + 977 * i + rank)
-            return (torch.randn(bs, 3, 32, 32, generator=g), torch.randint(0, 10, (bs,), generator=g))
+            x = torch.randn(bs, 3, 32, 32, generator=g)
+            return (x, (x.flatten(1) @ _tw).argmax(1))
 
         def fwd(batch):
             x, y = batch
@@ -90,13 +94,17 @@ def run_reference(args, MODELS) -> dict:
         net = net.to(dev)
         ctc = torch.nn.CTCLoss(blank=0, reduction="sum", zero_infinity=True)    # warpctc_pytorch is not installable
 
+        _tpl = torch.randn(29, 161, generator=torch.Generator().manual_seed(4243))
+
         def make_batch(i):
+            # same synthetic task as the other arm: each character = 12 frames of its spectral template + noise
             g = torch.Generator().manual_seed(1234 + 977 * i + rank)
-            T = int(torch.randint(100, 401, (1,), generator=g))
-            x = torch.randn(bs, 1, 161, T, generator=g)
-            lens = torch.full((bs,), T, dtype=torch.int32)
-            tl = max(T // 12, 2)
+            tl = int(torch.randint(8, 34, (1,), generator=g))
+            T = 12 * tl
             tg = torch.randint(1, 29, (bs * tl,), generator=g, dtype=torch.int32)
+            base = _tpl[tg.long()].view(bs, tl, 161).repeat_interleave(12, dim=1).transpose(1, 2)    # [bs,161,T]
+            x = (base + 0.5 * torch.randn(base.shape, generator=g)).unsqueeze(1).contiguous()
+            lens = torch.full((bs,), T, dtype=torch.int32)
             return (x, lens, tg, torch.full((bs,), tl, dtype=torch.int32))
 
         def fwd(batch):

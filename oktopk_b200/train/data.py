@@ -22,39 +22,62 @@ from torch.utils.data import DataLoader, Dataset, DistributedSampler
 DATASET_CLASSES = {"cifar10": 10, "imagenet": 1000, "mnist": 10, "an4": 29, "ptb": 10000, "wikipedia": 30522}
 
 
+def teacher_labels(images: torch.Tensor, classes: int, seed: int = 4242) -> torch.Tensor:
+    """Learnable synthetic labels: argmax of a fixed random linear map of the image.  (Purely random labels make
+    training collapse to the uniform prediction within ~50 steps, after which gradients -- and the sparse selection
+    the benchmark is about -- degenerate.)"""
+    g = torch.Generator().manual_seed(seed)
+    w = torch.randn(images[0].numel(), classes, generator=g)
+    return (images.flatten(1) @ w).argmax(1)
+
+
 class SyntheticImages(Dataset):
     def __init__(self, n: int, shape: Tuple[int, int, int], classes: int, seed: int = 0):
         g = torch.Generator().manual_seed(seed)
         self.n, self.shape, self.classes = n, shape, classes
         # a small pool of distinct images re-indexed cyclically keeps host memory bounded
         self.pool = torch.randn((min(n, 2048),) + shape, generator=g)
-        self.labels = torch.randint(0, classes, (n,), generator=g)
+        self.pool_labels = teacher_labels(self.pool, classes)
 
     def __len__(self):
         return self.n
 
     def __getitem__(self, i):
-        return self.pool[i % self.pool.size(0)], self.labels[i]
+        j = i % self.pool.size(0)
+        return self.pool[j], self.pool_labels[j]
+
+
+def an4_templates(labels: int = 29, seed: int = 4243) -> torch.Tensor:
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(labels, 161, generator=g)
+
+
+def an4_utterance(target: torch.Tensor, frames_per_char: int, templates: torch.Tensor, gen: torch.Generator,
+                  noise: float = 0.5) -> torch.Tensor:
+    """A learnable synthetic utterance: every character is ``frames_per_char`` frames of its spectral template + noise."""
+    base = templates[target.long()].repeat_interleave(frames_per_char, dim=0).t()          # [161, T]
+    return base + noise * torch.randn(base.shape, generator=gen)
 
 
 class SyntheticAN4(Dataset):
-    """Variable-length spectrogram + transcript pairs (AN4: ~1-5 s utterances, 161 frequency bins)."""
+    """Variable-length spectrogram + transcript pairs (AN4: ~1-5 s utterances, 161 frequency bins, 100-400 frames)."""
 
     def __init__(self, n: int = 948, min_frames: int = 100, max_frames: int = 400, seed: int = 0, labels: int = 29):
         g = torch.Generator().manual_seed(seed)
         self.n = n
-        self.frames = torch.randint(min_frames, max_frames + 1, (n,), generator=g)
-        self.tlen = torch.clamp(self.frames // 12, min=2)
+        self.fpc = 12
+        self.tlen = torch.randint(max(min_frames // self.fpc, 2), max_frames // self.fpc + 1, (n,), generator=g)
+        self.frames = self.tlen * self.fpc
         self.seed, self.labels = seed, labels
+        self.templates = an4_templates(labels)
 
     def __len__(self):
         return self.n
 
     def __getitem__(self, i):
         g = torch.Generator().manual_seed(self.seed * 1_000_003 + i)
-        spect = torch.randn(161, int(self.frames[i]), generator=g)
         target = torch.randint(1, self.labels, (int(self.tlen[i]),), generator=g)
-        return spect, target
+        return an4_utterance(target, self.fpc, self.templates, g), target
 
 
 def an4_collate(batch):

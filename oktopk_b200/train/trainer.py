@@ -52,6 +52,11 @@ class Trainer:
                  model_kwargs: Optional[dict] = None, autocast: Optional[str] = None):
         self.world = world or _world()
         self.rank, self.nworkers = self.world.rank, self.world.size
+        # The host side of a step is tiny tensor ops (collate 16 images, one pinned copy): on a many-core box an
+        # unconstrained intra-op pool costs milliseconds of thread wake-ups per op.  torchrun already pins
+        # OMP_NUM_THREADS=1 per rank; do the equivalent for a plain `python` launch.
+        if "OMP_NUM_THREADS" not in os.environ and torch.get_num_threads() > 4:
+            torch.set_num_threads(4)
         self.dnn = dnn
         self.dataset = (dataset or _DATASET_OF.get(dnn, "cifar10")).lower()
         self.batch_size, self.lr, self.nsteps_update, self.max_epochs = batch_size, lr, nsteps_update, max_epochs
