@@ -310,15 +310,94 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
                     st_stream_f4(g4 + v, make_float4(0.f, 0.f, 0.f, 0.f));
                 }
             }
+            // ---- selection: one slot reservation per (warp, trip, destination) ------------------------------
+            // 16 element flags per lane -> 16 ballots; the warp's trip covers 4 windows of 128 consecutive elements,
+            // which (regions being contiguous ranges) almost always belong to ONE destination, so the append costs
+            // one global atomic per trip instead of one per selected vector component.
+            unsigned msk[kPackTile * 4];
+            unsigned mybits = 0u;
+            int tot = 0;
 #pragma unroll
             for (int u = 0; u < kPackTile; ++u) {
-                const int v = base + u * kThreads + tid;
-                const float m4 = fmaxf(fmaxf(fabsf(a[u].x), fabsf(a[u].y)), fmaxf(fabsf(a[u].z), fabsf(a[u].w)));
-                if (__ballot_sync(0xffffffffu, in[u] && m4 > thr_sel) == 0) continue;
-                emit(4 * v + 0, a[u].x, in[u]);
-                emit(4 * v + 1, a[u].y, in[u]);
-                emit(4 * v + 2, a[u].z, in[u]);
-                emit(4 * v + 3, a[u].w, in[u]);
+                const float xs[4] = {a[u].x, a[u].y, a[u].z, a[u].w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const bool pred = in[u] && fabsf(xs[c]) > thr_sel;
+                    const unsigned m = __ballot_sync(0xffffffffu, pred);
+                    msk[u * 4 + c] = m;
+                    tot += __popc(m);
+                    if (pred) mybits |= 1u << (u * 4 + c);
+                }
+            }
+            if (tot == 0) continue;
+            // guard ladder / residual side effects of my selected elements
+#pragma unroll
+            for (int u = 0; u < kPackTile; ++u) {
+                const float xs[4] = {a[u].x, a[u].y, a[u].z, a[u].w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (mybits & (1u << (u * 4 + c))) {
+                        const float ax = fabsf(xs[c]);
+                        gc[0]++;
+                        if (!two_pass) {
+#pragma unroll
+                            for (int j = 1; j < kGuardMax; ++j) gc[j] += (j <= p.guard_loops && ax > lad[j]) ? 1 : 0;
+                        }
+                        if (p.residual_mode != RES_OKTOPK) p.res[4 * (base + u * kThreads + tid) + c] = 0.f;
+                    }
+                }
+            }
+            const int e_first = 4 * (base + (warp << 5));
+            const int e_last = min(n - 1, 4 * (base + (kPackTile - 1) * kThreads + (warp << 5) + 31) + 3);
+            const int dlo = region_of(s_edges, P, e_first), dhi = region_of(s_edges, P, e_last);
+            for (int d = dlo; d <= dhi; ++d) {
+                unsigned md[kPackTile * 4];
+                unsigned mine = mybits;
+                int cnt = 0;
+                if (dlo == dhi) {
+#pragma unroll
+                    for (int q = 0; q < kPackTile * 4; ++q) { md[q] = msk[q]; cnt += __popc(md[q]); }
+                } else {
+                    const int lo_d = s_edges[d], hi_d = s_edges[d + 1];
+                    mine = 0u;
+#pragma unroll
+                    for (int u = 0; u < kPackTile; ++u) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const int i = 4 * (base + u * kThreads + tid) + c;
+                            const bool pd = ((mybits >> (u * 4 + c)) & 1u) && i >= lo_d && i < hi_d;
+                            md[u * 4 + c] = __ballot_sync(0xffffffffu, pd);
+                            cnt += __popc(md[u * 4 + c]);
+                            if (pd) mine |= 1u << (u * 4 + c);
+                        }
+                    }
+                }
+                if (cnt == 0) continue;
+                int run = 0;
+                if (lane == 0) run = atomicAdd(&st->send_cursor[d], cnt);
+                run = __shfl_sync(0xffffffffu, run, 0);
+                int* sidx = send_idx(me, p.L, P, par, d);
+                float* sval = send_val(me, p.L, P, par, d);
+                const int off_d = s_edges[d];
+                const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+                for (int u = 0; u < kPackTile; ++u) {
+                    const float xs[4] = {a[u].x, a[u].y, a[u].z, a[u].w};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int q = u * 4 + c;
+                        if ((mine >> q) & 1u) {
+                            const int pos = run + __popc(md[q] & lt);
+                            if (pos < cap) {
+                                sidx[pos] = 4 * (base + u * kThreads + tid) + c - off_d;
+                                sval[pos] = xs[c];
+                            } else {
+                                dropped++;
+                            }
+                        }
+                        run += __popc(md[q]);
+                    }
+                }
             }
         }
         if (blockIdx.x == 0 && warp == 0 && (n & 3)) {
