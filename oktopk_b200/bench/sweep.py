@@ -136,7 +136,8 @@ def run(args) -> List[Dict]:
                        "link_GBs": moved / (ms * 1e-3) / 1e9,
                        "hbm_frac": None if scheme in ("dense", "nccl") else (16.0 * n / (ms * 1e-3) / 1e9) / hbm,
                        "local_count": stats.get("local_count"), "global_count": stats.get("global_count"),
-                       "overflow": (stats.get("overflow_send", 0) + stats.get("overflow_gather", 0)) if stats else None}
+                       "overflow": (stats.get("overflow_send", 0) + stats.get("overflow_gather", 0)) if stats else None,
+                       "phase_us": {k2: round(v2, 1) for k2, v2 in stats.get("phase_us", {}).items()} if stats else None}
                 rows.append(row)
                 if rank == 0:
                     print(json.dumps(row), flush=True)

@@ -87,6 +87,11 @@ static py::dict read_state(uint64_t st, int P, uint64_t stream) {
     d["recv_total"] = s->stat_recv_total; d["gather_total"] = s->stat_gather_total;
     d["overflow_send"] = s->stat_overflow_send; d["overflow_gather"] = s->stat_overflow_gather;
     d["fault"] = s->fault;
+    // phase durations of the last fused call in microseconds: pack, reduce-scatter, global select, allgather+finalise
+    auto us = [&](int a, int b) { return s->t_phase[b] >= s->t_phase[a] ? (double)(s->t_phase[b] - s->t_phase[a]) * 1e-3 : 0.0; };
+    py::dict ph;
+    ph["pack"] = us(0, 1); ph["reduce"] = us(1, 2); ph["gselect"] = us(2, 3); ph["final"] = us(3, 4); ph["total"] = us(0, 4);
+    d["phase_us"] = ph;
     return d;
 }
 
@@ -118,6 +123,9 @@ static void oktopk_run(uint64_t g, uint64_t res, uint64_t st, const std::vector<
     OktParams p;
     std::memset(&p, 0, sizeof(p));
     p.g = P_<float>(g); p.res = P_<float>(res); p.st = P_<OktState>(st);
+    if (!o.contains("cand") || !o.contains("ccap")) throw std::runtime_error("oktopk_run: candidate scratch missing");
+    p.cand = P_<int>(o["cand"].cast<uint64_t>()); p.ccap = o["ccap"].cast<int>();
+    p.cand_mode = o.contains("cand_mode") ? o["cand_mode"].cast<int>() : 1;
     fill_peers(p.peers, peers);
     p.P = (int)peers.size(); p.rank = rank; p.n = n; p.k = k;
     p.L = make_layout(p.P, cap, gcap);

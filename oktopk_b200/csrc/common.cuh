@@ -179,6 +179,11 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, ui
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
         ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// order ALL prior generic-proxy accesses (global data other CTAs produced before the grid barrier, and this CTA's
+// shared-memory reads of a ring stage) before subsequent async-proxy (TMA) operations
+__device__ __forceinline__ void fence_proxy_async_all() {
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
 // make generic-proxy smem reads that preceded this point ordered before later async-proxy writes
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -214,6 +219,18 @@ __device__ __forceinline__ int warp_append(int* cursor, bool pred) {
     int base = 0;
     if (lane_id() == leader) base = atomicAdd(cursor, __popc(m));
     base = __shfl_sync(0xffffffffu, base, leader);
+    return pred ? base + __popc(m & ((1u << lane_id()) - 1u)) : -1;
+}
+
+// Same for a possibly partially-active warp (tail of a strided loop): aggregates over the active lanes only.
+__device__ __forceinline__ int warp_append_active(int* cursor, bool pred) {
+    const unsigned act = __activemask();
+    const unsigned m = __ballot_sync(act, pred);
+    if (m == 0) return -1;
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane_id() == leader) base = atomicAdd(cursor, __popc(m));
+    base = __shfl_sync(act, base, leader);
     return pred ? base + __popc(m & ((1u << lane_id()) - 1u)) : -1;
 }
 

@@ -167,6 +167,39 @@ static __device__ float grid_kth_abs(const Seg* segs, int nseg, bool remote, uin
 }
 
 // ------------------------------------------------------------------------------------------
+// TMA-fed streaming read: the CTA walks its share of `nvec` float4 (tiles of kTileV float4 dealt round-robin to
+// CTAs) through a STAGES-deep shared-memory ring.  One elected thread arms a stage's mbarrier and issues the
+// cp.async.bulk load STAGES-1 tiles ahead; all threads consume the landed tile from shared memory through
+// body(tile_smem, first_vec_of_tile).  `bars` must be STAGES freshly initialised mbarriers used by nobody else.
+// ------------------------------------------------------------------------------------------
+constexpr int kTileV = kPackTile * kThreads;      // float4 per tile
+
+template <int STAGES, class Body>
+__device__ __forceinline__ void tma_stream_tiles(const float4* src, int nvec, float4* ring, uint64_t* bars, Body&& body) {
+    const int ntiles = (nvec + kTileV - 1) / kTileV;
+    const int G = gridDim.x;
+    const int nmine = (ntiles > (int)blockIdx.x) ? (ntiles - (int)blockIdx.x + G - 1) / G : 0;
+    auto arm = [&](int j) {                       // thread 0 only
+        const int tile = blockIdx.x + j * G;
+        const int stg = j % STAGES;
+        const uint32_t bytes = (uint32_t)min(kTileV, nvec - tile * kTileV) * 16u;
+        fence_proxy_async_all();
+        mbar_expect_tx(&bars[stg], bytes);
+        tma_load_1d(ring + stg * kTileV, src + (size_t)tile * kTileV, bytes, &bars[stg]);
+    };
+    if (threadIdx.x == 0)
+        for (int j = 0; j < min(nmine, STAGES - 1); ++j) arm(j);
+    for (int j = 0; j < nmine; ++j) {
+        __syncthreads();                          // the stage consumed last iteration is drained: re-arm it
+        if (threadIdx.x == 0 && j + STAGES - 1 < nmine) arm(j + STAGES - 1);
+        const int stg = j % STAGES;
+        mbar_wait(&bars[stg], (uint32_t)(j / STAGES) & 1u);
+        body(ring + stg * kTileV, (blockIdx.x + j * G) * kTileV);
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
 // chunk puller: double-buffered TMA bulk copies of (idx,val) chunks from (possibly remote) slots
 // ------------------------------------------------------------------------------------------
 struct PullSmem {
@@ -205,7 +238,7 @@ __device__ __forceinline__ void pull_chunks(const ChunkSrc* srcs, int nsrc, bool
             locate(c0 + j * G, s, off);
             uint32_t it = pipe_it + j;
             int stg = it & 1;
-            fence_proxy_async_smem();
+            fence_proxy_async_all();
             mbar_expect_tx(&sm->bar[stg], 2u * kChunk * 4u);
             tma_load_1d(sm->idx[stg], srcs[s].idx + off, kChunk * 4u, &sm->bar[stg]);
             tma_load_1d(sm->val[stg], srcs[s].val + off, kChunk * 4u, &sm->bar[stg]);

@@ -37,6 +37,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
     __shared__ float s_thr[OKT_MAXP];
     __shared__ int s_misc[OKT_MAXP * 2 + 4];
     __shared__ __align__(128) PullSmem s_pull;
+    __shared__ __align__(8) uint64_t s_pk_bar[kPackStages];
+    __shared__ __align__(8) uint64_t s_sc_bar[kScanStages];
+    extern __shared__ __align__(128) float4 dyn_pk[];       // TMA ring of the streaming pass (kPackSmemBytes)
 
     OktState* st = p.st;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -53,6 +56,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
     if (tid == 0) {
         mbar_init(&s_pull.bar[0], 1);
         mbar_init(&s_pull.bar[1], 1);
+        for (int q = 0; q < kPackStages; ++q) mbar_init(&s_pk_bar[q], 1);
+        for (int q = 0; q < kScanStages; ++q) mbar_init(&s_sc_bar[q], 1);
         mbar_fence_init();
     }
     __syncthreads();
@@ -223,6 +228,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
     // region edges for this call
     if (tid <= P) s_edges[tid] = st->edges[tid];
     __syncthreads();
+    // per-phase device timestamps (observability: the reference's _compression/_allreduce wall-clock timers)
+    auto stamp = [&](int slot) { if (blockIdx.x == 0 && tid == 0) st->t_phase[slot] = globaltimer_ns(); };
+    stamp(0);
 
     // ======================================================================== PH_PACK
     if (p.phase_begin <= PH_PACK && PH_PACK < p.phase_end) {
@@ -275,36 +283,46 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
             if (p.residual_mode != RES_OKTOPK && pred) p.res[i] = 0.f;   // classic local error feedback
         };
 
-        // Streaming pass, kPackTile independent 128-bit vectors per thread per trip: all loads of a trip are
-        // issued before the first dependent instruction (bytes in flight per SM = 512 thr x 2 x 4 x 16 B = 64 KB),
-        // stores are write-through streaming, and the (rare: density ~ 1e-3) selections go through the
-        // warp-aggregated slot append.  16 B/element of HBM traffic, the roofline floor of the whole call.
-        const int trip = gridDim.x * kThreads * kPackTile;
-        for (int base = blockIdx.x * kThreads * kPackTile; base < n4; base += trip) {
+        // Streaming pass fed by TMA: the CTA walks its tiles (kPackTile x 512 float4 = 16 KB of the gradient + 16 KB of
+        // the residual each) through a kPackStages-deep shared-memory ring.  One elected thread arms the stage's mbarrier
+        // (expect_tx) and issues the two cp.async.bulk loads kPackStages-1 tiles ahead, so ~96 KB of reads per SM are in
+        // flight independent of occupancy/register budget; consumers read the tile with conflict-free LDS.128, write the
+        // accumulator / the zeroed bucket back with streaming 128-bit stores (posted), and run the selection.
+        // 16 B/element of HBM traffic: the roofline floor of the whole call.
+        float4* pk_r = dyn_pk;                                          // [kPackStages][kTileV]
+        float4* pk_g = dyn_pk + kPackStages * kTileV;                   // [kPackStages][kTileV]
+        const int ntiles = (n4 + kTileV - 1) / kTileV;
+        const int G = gridDim.x;
+        const int nmine = (ntiles > (int)blockIdx.x) ? (ntiles - (int)blockIdx.x + G - 1) / G : 0;
+        auto arm = [&](int j) {                                         // thread 0 only
+            const int tile = blockIdx.x + j * G;
+            const int stg = j % kPackStages;
+            const uint32_t bytes = (uint32_t)min(kTileV, n4 - tile * kTileV) * 16u;
+            fence_proxy_async_all();
+            mbar_expect_tx(&s_pk_bar[stg], two_pass ? bytes : 2u * bytes);
+            tma_load_1d(pk_r + stg * kTileV, r4 + (size_t)tile * kTileV, bytes, &s_pk_bar[stg]);
+            if (!two_pass) tma_load_1d(pk_g + stg * kTileV, g4 + (size_t)tile * kTileV, bytes, &s_pk_bar[stg]);
+        };
+        if (tid == 0)
+            for (int j = 0; j < min(nmine, kPackStages - 1); ++j) arm(j);
+        for (int j = 0; j < nmine; ++j) {
+            __syncthreads();                                            // stage (j-1) % kPackStages is drained: re-arm it
+            if (tid == 0 && j + kPackStages - 1 < nmine) arm(j + kPackStages - 1);
+            const int stg = j % kPackStages;
+            mbar_wait(&s_pk_bar[stg], (uint32_t)(j / kPackStages) & 1u);
+            const int base = (blockIdx.x + j * G) * kTileV;
             float4 a[kPackTile];
-            float4 r[kPackTile];
             bool in[kPackTile];
 #pragma unroll
             for (int u = 0; u < kPackTile; ++u) {
                 const int v = base + u * kThreads + tid;
                 in[u] = v < n4;
                 a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                r[u] = a[u];
                 if (in[u]) {
-                    if (two_pass) {
-                        a[u] = ld_stream_f4(r4 + v);
-                    } else {
-                        a[u] = ld_stream_f4(g4 + v);
-                        r[u] = ld_stream_f4(r4 + v);
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < kPackTile; ++u) {
-                const int v = base + u * kThreads + tid;
-                if (in[u]) {
+                    a[u] = pk_r[stg * kTileV + u * kThreads + tid];
                     if (!two_pass) {
-                        a[u].x += r[u].x; a[u].y += r[u].y; a[u].z += r[u].z; a[u].w += r[u].w;
+                        const float4 gq = pk_g[stg * kTileV + u * kThreads + tid];
+                        a[u].x += gq.x; a[u].y += gq.y; a[u].z += gq.z; a[u].w += gq.w;
                         st_stream_f4(r4 + v, a[u]);
                     }
                     st_stream_f4(g4 + v, make_float4(0.f, 0.f, 0.f, 0.f));
@@ -427,6 +445,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
         int dsum = warp_sum(dropped);
         if (lane == 0 && dsum) atomicAdd(&st->stat_overflow_send, dsum);
         if (PH_PACK + 1 < p.phase_end) grid_sync(&st->bar);
+        stamp(1);
     }
 
     // ======================================================================== PH_PUBLISH_RS
@@ -467,8 +486,22 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
         const int len_me = s_edges[rank + 1] - off_me;
         float* greg = p.g + off_me;
         int pulled = 0;
+        // Scatter-add with first-touch detection: the pack pass zeroed the bucket, so the contribution that finds
+        // 0.0 is the first one of its index; that index goes on the candidate list the global selection walks, which
+        // makes the selection O(#entries) instead of a scan of the whole region (4n/P bytes).  (A sum that passes
+        // through exactly 0.0 can list an index twice; the selection claims each index with an exchange, so a
+        // duplicate is seen as empty.)
         auto add = [&](int s_local, int idx, float val, const float* thr_of) {
-            if (fabsf(val) > thr_of[s_local] && (unsigned)idx < (unsigned)len_me) red_add_f32(greg + idx, val);
+            const bool ok = fabsf(val) > thr_of[s_local] && (unsigned)idx < (unsigned)len_me;
+            if (p.cand_mode) {
+                float old = 1.f;
+                if (ok) old = atomicAdd(greg + idx, val);
+                const bool first = ok && old == 0.f;
+                const int pos = warp_append_active(&st->cand_cursor, first);
+                if (first && pos < p.ccap) p.cand[pos] = idx;
+            } else if (ok) {
+                red_add_f32(greg + idx, val);               // high density: fire-and-forget reduction, region scanned later
+            }
             pulled++;
         };
         if (!p.deterministic) {
@@ -495,6 +528,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
         int psum = warp_sum(pulled);
         if (lane == 0 && psum) atomicAdd(&st->stat_recv_total, psum);
         if (PH_REDUCE + 1 < p.phase_end) grid_sync(&st->bar);
+        stamp(2);
     }
 
     // ======================================================================== PH_GSELECT
@@ -506,59 +540,99 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
         float* gv = gat_val(me, p.L, par);
         const float fP = (float)P;
         int dropped = 0;
-        // one element: select, append to my gather slot, leave result/P (or 0) in place; converged per warp
-        auto visit = [&](int i, float v, bool in) -> float {
-            const bool nz = in && v != 0.f;
-            const bool sel = (p.global_mode == GLB_THRESHOLD) ? (nz && fabsf(v) > gthr) : nz;
-            const int pos = warp_append(&st->gather_cursor, sel);
-            bool kept = false;
-            if (sel) {
-                if (pos < gcap) { gi[pos] = i; gv[pos] = v; kept = true; }
-                else dropped++;
+        if (p.cand_mode) {
+            // Low density: walk the candidate list of the reduce phase (every index of my region that received a
+            // contribution): claim the reduced value (exchange with 0: the bucket stays all-zero until the final phase
+            // writes the kept entries), select, append to my gather slot.  No scan of the region.
+            const int ncand = min(*reinterpret_cast<volatile int*>(&st->cand_cursor), p.ccap);
+            const int ncr = (ncand + 31) / 32 * 32;
+            for (int c = gtid; c < ncr; c += gthreads) {
+                const bool in = c < ncand;
+                const int i = in ? __ldcg(p.cand + c) : 0;
+                const float v = in ? atomicExch(p.g + lo + i, 0.f) : 0.f;
+                const bool nz = in && v != 0.f;
+                const bool sel = (p.global_mode == GLB_THRESHOLD) ? (nz && fabsf(v) > gthr) : nz;
+                const int pos = warp_append(&st->gather_cursor, sel);
+                if (sel) {
+                    if (pos < gcap) { gi[pos] = lo + i; gv[pos] = v; }
+                    else dropped++;
+                }
             }
-            return (kept && p.global_mode != GLB_EXACT_TOPK) ? v / fP : 0.f;
-        };
-        // scalar head / tail so that the body is 16-byte aligned (region edges are arbitrary)
-        const int first = min(hi, (lo + 3) & ~3), last = max(first, hi & ~3);
-        if (blockIdx.x == 0 && warp == 0) {
-            for (int part = 0; part < 2; ++part) {
-                const int b0 = part ? last : lo, b1 = part ? hi : first;
-                const int i = b0 + lane;
-                const bool in = i < b1;                       // at most 3 elements per part
+        } else {
+            // High density (a large fraction of the region is non-zero): stream the region through the TMA ring, one
+            // gather-slot reservation per warp per tile, and zero what was read (the final phase writes the kept
+            // entries).  Scalar head / tail so that the body is 16-byte aligned (region edges are arbitrary).
+            auto visit1 = [&](int i, bool in) {
                 const float v = in ? __ldcg(p.g + i) : 0.f;
-                const float o = visit(i, v, in);
-                if (in && v != 0.f) p.g[i] = o;
+                const bool nz = in && v != 0.f;
+                const bool sel = (p.global_mode == GLB_THRESHOLD) ? (nz && fabsf(v) > gthr) : nz;
+                const int pos = warp_append(&st->gather_cursor, sel);
+                if (sel) {
+                    if (pos < gcap) { gi[pos] = i; gv[pos] = v; }
+                    else dropped++;
+                }
+                if (nz) p.g[i] = 0.f;
+            };
+            const int first = min(hi, (lo + 3) & ~3), last = max(first, hi & ~3);
+            if (blockIdx.x == 0 && warp == 0) {
+                visit1(lo + lane, lo + lane < first);
+                visit1(last + lane, last + lane < hi);
             }
-        }
-        const int nv = (last - first) >> 2;
-        const float4* gv4 = reinterpret_cast<const float4*>(p.g + first);
-        const int nvr = (nv + 31) / 32 * 32;
-        for (int q0 = blockIdx.x * kThreads * kScanTile; q0 < nvr; q0 += gridDim.x * kThreads * kScanTile) {
-            float4 a[kScanTile];
-            bool in[kScanTile];
+            const int nv = (last - first) >> 2;
+            const float4* gv4 = reinterpret_cast<const float4*>(p.g + first);
+            tma_stream_tiles<kScanStages>(gv4, nv, dyn_pk, s_sc_bar, [&](const float4* tile, int q0) {
+                float4 a[kPackTile];
+                unsigned nzbits = 0u, selbits = 0u;
+                int tot = 0;
 #pragma unroll
-            for (int u = 0; u < kScanTile; ++u) {
-                const int q = q0 + u * kThreads + tid;
-                in[u] = q < nv;
-                a[u] = in[u] ? __ldcg(gv4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+                for (int u = 0; u < kPackTile; ++u) {
+                    const bool in = q0 + u * kThreads + tid < nv;
+                    a[u] = in ? tile[u * kThreads + tid] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float xs[4] = {a[u].x, a[u].y, a[u].z, a[u].w};
 #pragma unroll
-            for (int u = 0; u < kScanTile; ++u) {
-                const int q = q0 + u * kThreads + tid;
-                const bool any = in[u] && (a[u].x != 0.f || a[u].y != 0.f || a[u].z != 0.f || a[u].w != 0.f);
-                if (__ballot_sync(0xffffffffu, any) == 0) continue;
-                const int i = first + 4 * q;
-                float4 o;
-                o.x = visit(i + 0, a[u].x, in[u]);
-                o.y = visit(i + 1, a[u].y, in[u]);
-                o.z = visit(i + 2, a[u].z, in[u]);
-                o.w = visit(i + 3, a[u].w, in[u]);
-                if (any) *reinterpret_cast<float4*>(p.g + i) = o;
-            }
+                    for (int c = 0; c < 4; ++c) {
+                        const bool nz = in && xs[c] != 0.f;
+                        const bool sel = (p.global_mode == GLB_THRESHOLD) ? (nz && fabsf(xs[c]) > gthr) : nz;
+                        if (nz) nzbits |= 1u << (u * 4 + c);
+                        if (sel) selbits |= 1u << (u * 4 + c);
+                        tot += __popc(__ballot_sync(0xffffffffu, sel));
+                    }
+                }
+                if (__ballot_sync(0xffffffffu, nzbits != 0u) == 0u) return;       // nothing landed in this span
+                int run = 0;
+                if (tot != 0) {
+                    if (lane == 0) run = atomicAdd(&st->gather_cursor, tot);
+                    run = __shfl_sync(0xffffffffu, run, 0);
+                }
+                const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+                for (int u = 0; u < kPackTile; ++u) {
+                    const float xs[4] = {a[u].x, a[u].y, a[u].z, a[u].w};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const bool sel = (selbits >> (u * 4 + c)) & 1u;
+                        const unsigned m = __ballot_sync(0xffffffffu, sel);
+                        if (sel) {
+                            const int pos = run + __popc(m & lt);
+                            if (pos < gcap) {
+                                gi[pos] = first + 4 * (q0 + u * kThreads + tid) + c;
+                                gv[pos] = xs[c];
+                            } else {
+                                dropped++;
+                            }
+                        }
+                        run += __popc(m);
+                    }
+                    if ((nzbits >> (u * 4)) & 0xfu)
+                        *reinterpret_cast<float4*>(p.g + first + 4 * (q0 + u * kThreads + tid)) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            });
         }
+        (void)fP;
         int dsum = warp_sum(dropped);
         if (lane == 0 && dsum) atomicAdd(&st->stat_overflow_gather, dsum);
         if (PH_GSELECT + 1 < p.phase_end) grid_sync(&st->bar);
+        stamp(3);
     }
 
     // ======================================================================== PH_PUBLISH_AG
@@ -567,7 +641,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
         __syncthreads();
         if (tid < P) st_release_sys_u64(ag_mbox(p.peers[tid], p.L, par, rank), make_mail(epoch, (uint32_t)s_misc[0]));
         __syncthreads();
-        if (tid == 0) st->gather_cursor = 0;
+        if (tid == 0) { st->gather_cursor = 0; st->cand_cursor = 0; }
     }
 
     // ======================================================================== PH_FINAL
@@ -607,7 +681,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
             bool keep = exact ? (fabsf(val) >= gsel) : true;
             if (!keep) return;
             kept_cnt++;
-            if (exact || src_rank[sl] != rank) p.g[idx] = val / fP;
+            p.g[idx] = val / fP;             // the bucket is all-zero here: every kept entry (own region included) lands now
             if (p.residual_mode == RES_OKTOPK) {
                 float r = p.res[idx];
                 if (fabsf(r) > thr_used) p.res[idx] = 0.f;
@@ -618,6 +692,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
         grid_sync(&st->bar);
         if (blockIdx.x == 0 && tid == 0) {
             st->epoch = epoch;
+            st->t_phase[4] = globaltimer_ns();
             st->stat_gather_total = T;
         }
     }
@@ -642,15 +717,24 @@ __global__ void __launch_bounds__(kThreads, 2) kth_abs_kernel(const float* x, in
 int okt_max_coop_grid(int device) {
     int sms = 0, per = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, oktopk_fused_kernel, kThreads, 0);
+    cudaFuncSetAttribute(oktopk_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPackSmemBytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, oktopk_fused_kernel, kThreads, kPackSmemBytes);
     if (per < 1) per = 1;
     if (per > kCtasPerSm) per = kCtasPerSm;
     return sms * per;
 }
 
 cudaError_t launch_oktopk(const OktParams& p, int grid, cudaStream_t stream) {
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(oktopk_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPackSmemBytes);
+        if (e != cudaSuccess) return e;
+        attr_set[dev] = true;
+    }
     void* args[] = {(void*)&p};
-    return cudaLaunchCooperativeKernel((void*)oktopk_fused_kernel, dim3(grid), dim3(kThreads), args, 0, stream);
+    return cudaLaunchCooperativeKernel((void*)oktopk_fused_kernel, dim3(grid), dim3(kThreads), args, kPackSmemBytes, stream);
 }
 
 cudaError_t launch_kth_abs(const float* x, int n, int k, OktState* st, float* out_thr, int grid, cudaStream_t stream) {

@@ -18,8 +18,10 @@ constexpr int kHistBins = 2048;           // 11-bit radix digit
 constexpr int kMaxWarpsTotal = 16384;     // per-warp counters for the quantile cuts
 constexpr int kGuardMax = 8;
 constexpr int kCtasPerSm = 1;           // persistent kernels: one 512-thread CTA per SM (<= 128 registers/thread)
-constexpr int kPackTile = 4;            // 128-bit vectors per thread per trip of the streaming pass
-constexpr int kScanTile = 4;            // same for the region scan of the global selection
+constexpr int kPackTile = 2;            // 128-bit vectors per thread per tile of the streaming pass
+constexpr int kPackStages = 4;          // TMA ring depth of the streaming pass
+constexpr int kPackSmemBytes = kPackStages * 2 * kPackTile * kThreads * 16;   // (grad + residual) tiles: 128 KB
+constexpr int kScanStages = 2 * kPackStages;   // the region scan reuses the whole ring as 8 single-array stages
 
 // ---- device-resident, zero-initialised, one per bucket ---------------------------------------
 struct OktState {
@@ -31,6 +33,7 @@ struct OktState {
     int edges[OKT_MAXP + 1];              // region edges, edges[0] = 0, edges[P] = n
     int send_cursor[OKT_MAXP];            // per-destination slot cursors (reset in-kernel)
     int gather_cursor;
+    int cand_cursor;                      // first-touch candidate list of the reduce phase (reset in-kernel)
     int guard_counts[kGuardMax];          // #(|acc| > thr0 * f^j)
     uint32_t sel_prefix;                  // radix-select running prefix / remaining rank
     uint32_t sel_krem;
@@ -44,6 +47,7 @@ struct OktState {
     int stat_overflow_gather;
     int stat_mode;
     int fault;                            // FaultCode of the first bounded wait that timed out (0 = healthy)
+    unsigned long long t_phase[8];        // globaltimer stamps: 0 start(after local phase) 1 pack 2 reduce 3 gselect 4 end
     double gs_sum, gs_sumsq;              // Gaussiank moments
     uint32_t hist[kHistBins];
     int wcounts[kMaxWarpsTotal];
@@ -103,6 +107,9 @@ struct OktParams {
     float* g;            // gradient bucket (result written in place)
     float* res;          // residual / accumulator
     OktState* st;
+    int* cand;           // local scratch: region-local indices that received a contribution (capacity ccap)
+    int ccap;
+    int cand_mode;       // 1: first-touch candidate list (low density), 0: region scan (high density)
     char* peers[OKT_MAXP];   // every rank's symmetric block as mapped into this process
     SymmLayout L;
     int n, P, rank, k;

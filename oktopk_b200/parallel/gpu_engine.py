@@ -87,6 +87,9 @@ class CudaBucketEngine:
         self.state_ptr = C.dev_alloc_zero(C.state_bytes())
         self.dense_epoch_ptr = C.dev_alloc_zero(8 * self.dense_grid)
         self.residual = torch.zeros(self.n, dtype=torch.float32, device=self.device)
+        # first-touch candidate list of the reduce phase: at most one entry per pulled (idx,val) pair
+        self.ccap = int(min(_round_up(self.n, 32), self.P * self.cap))
+        self.cand = torch.zeros(self.ccap, dtype=torch.int32, device=self.device)
         self.host = SparseState(self.n, self.P)          # counter + (lazily refreshed) mirrors
         self._write_edges(self.host.region_offsets + [self.n])
         self._dist_state: Optional[SparseState] = None
@@ -142,7 +145,11 @@ class CudaBucketEngine:
         k = self.k_now(density)
         it = self.host.counter - cfg.warmup_iters
         o: Dict = {"pull_tma": 1 if cfg.pull_mode == "tma" else 0, "deterministic": int(cfg.deterministic),
-                   "split_phases": 0 if cfg.fused else 1, "timeout_s": float(cfg.peer_timeout_s)}
+                   "split_phases": 0 if cfg.fused else 1, "timeout_s": float(cfg.peer_timeout_s),
+                   "cand": self.cand.data_ptr(), "ccap": self.ccap,
+                   # global selection: candidate list when few entries land in a region (O(#entries) with atomics that
+                   # return), region scan when a large fraction of it is non-zero (O(n/P) streaming)
+                   "cand_mode": int(cfg.gselect_mode == "list" or (cfg.gselect_mode == "auto" and k * 200 <= self.n))}
         if compressor == "oktopk":
             o.update(
                 exact_local=int(it % cfg.local_recompute_interval == 0),

@@ -108,6 +108,18 @@ def test_oktopk_single_gpu_matches_oracle(n, fused, pull):
     _run_engine_vs_oracle("oktopk", n, 10, cfg)
 
 
+@pytest.mark.parametrize("mode", ["list", "scan"])
+@pytest.mark.parametrize("density", [0.002, 0.05])
+def test_oktopk_global_selection_paths(mode, density):
+    """Candidate-list and region-scan global selection are interchangeable (same result as the oracle)."""
+    from oktopk_b200.config import OkTopkConfig
+    cfg = OkTopkConfig(density=density, local_recompute_interval=4, global_recompute_interval=3, repartition_interval=8,
+                       gselect_mode=mode, slot_factor=64, gather_factor=64)
+    _run_engine_vs_oracle("oktopk", 1_000_003, 8, cfg)
+    if density == 0.05:
+        _run_engine_vs_oracle("topkSA", 300_001, 4, cfg)
+
+
 def test_oktopk_lstm_and_bert_presets():
     import oktopk_b200 as okt
     for preset in ("lstm_an4", "bert_base"):

