@@ -211,20 +211,20 @@ __global__ void __launch_bounds__(kThreads, 2) gather_scheme_kernel(const Gather
     if (tid < P) s_cnt[tid] = (int)wait_mailbox(ag_mbox(me, p.L, par, tid), epoch, SpinGuard{&st->fault, p.timeout_ns, FAULT_AG_TIMEOUT});
     __syncthreads();
     {
+        // Every rank reduces all P slots itself (no owner), so the order of the floating-point additions must be the
+        // same on every rank or the replicas drift apart by rounding: sources are processed in rank order with a grid
+        // barrier between them (indices are unique inside one slot, so there are no intra-source conflicts) -- the
+        // reference's P sequential scatter-adds (VGG/allreducer.py:510-518), bitwise identical on all ranks.
         int T = 0;
-        ChunkSrc srcs[OKT_MAXP];
-        for (int t = 0; t < P; ++t) {
-            const int s = (rank + t) % P;
-            srcs[t].idx = gat_idx(p.peers[s], p.L, par);
-            srcs[t].val = gat_val(p.peers[s], p.L, par);
-            srcs[t].count = s_cnt[s];
-            T += s_cnt[s];
-        }
         const float fP = (float)P;
-        pull_chunks(srcs, P, p.pull_tma != 0, &s_pull, pipe_it, [&](int, int idx, float val) {
-            if ((unsigned)idx < (unsigned)n) red_add_f32(p.g + idx, val / fP);
-        });
-        grid_sync(&st->bar);
+        for (int s = 0; s < P; ++s) {
+            ChunkSrc src{gat_idx(p.peers[s], p.L, par), gat_val(p.peers[s], p.L, par), s_cnt[s]};
+            T += s_cnt[s];
+            pull_chunks(&src, 1, p.pull_tma != 0, &s_pull, pipe_it, [&](int, int idx, float val) {
+                if ((unsigned)idx < (unsigned)n) red_add_f32(p.g + idx, val / fP);
+            });
+            grid_sync(&st->bar);
+        }
         if (blockIdx.x == 0 && tid == 0) {
             st->epoch = epoch;
             st->stat_gather_total = T;

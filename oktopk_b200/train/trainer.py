@@ -166,7 +166,10 @@ class Trainer:
             lengths = (in_pct * inputs.size(3)).int()
             out, out_lens = self.net(inputs, lengths)
             logp = F.log_softmax(out.transpose(0, 1), dim=-1)          # T x N x C
-            loss = self.criterion(logp, targets.cpu(), out_lens.cpu(), tsizes.cpu()) / inputs.size(0)
+            # int64 device targets => torch's native CTC kernels (int32 host targets would route to cuDNN's CTC, which
+            # has no zero_infinity handling and produced NaN gradients on synthetic utterances)
+            loss = self.criterion(logp.float(), targets.to(logp.device).long(), out_lens.to(logp.device).long(),
+                                  tsizes.to(logp.device).long()) / inputs.size(0)
             return loss, None
         if self.dataset == "ptb":
             x, y = batch

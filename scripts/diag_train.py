@@ -28,8 +28,15 @@ dnn, ds, bs, lr = M[a.model]
 cfg = okt.preset(preset_for(dnn), density=a.density, warmup_iters=a.warmup_iters)
 tr = Trainer(dnn=dnn, dataset=ds, batch_size=a.batch_size or bs, lr=a.lr or lr, compressor=a.compressor, density=a.density,
              compression=a.compressor != "none", cfg=cfg, world=w, cuda_graph=a.graph, t_total=100000, warmup=0.1)
+import math  # noqa: E402
+nan_at = None
 for i in range(a.steps):
     tr.train_step()
+    if nan_at is None and a.model == "lstman4":
+        lv = tr.last_loss()
+        if not math.isfinite(lv):
+            nan_at = i
+            print("!! non-finite loss %r first at step %d" % (lv, i), flush=True)
     if i % a.every == 0 or i == a.steps - 1:
         loss = tr.last_loss()
         st = tr.optimizer.comm_stats()
