@@ -227,13 +227,24 @@ class Prefetcher:
                     out.append(t)
             self.next_batch = tuple(out)
 
-    def next(self):
+    def next(self, defer: bool = False):
+        """The staged batch (device tensors).  With ``defer=True`` the host work for the FOLLOWING batch (collate, pinned
+        copy, H2D enqueue) is postponed until ``advance()``, which the trainer calls right after it has enqueued the step:
+        that work then overlaps the GPU executing the step instead of delaying its launch."""
+        if self.next_batch is None:
+            self._preload()
         if self.stream is not None:
             torch.cuda.current_stream().wait_stream(self.stream)
         batch = self.next_batch
+        self.next_batch = None
         if self.stream is not None:
             for t in batch:
                 if torch.is_tensor(t):
                     t.record_stream(torch.cuda.current_stream())
-        self._preload()
+        if not defer:
+            self._preload()
         return batch
+
+    def advance(self) -> None:
+        if self.next_batch is None:
+            self._preload()

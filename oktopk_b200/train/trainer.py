@@ -74,6 +74,8 @@ class Trainer:
         self.autocast = {"bf16": torch.bfloat16, "fp16": torch.float16}.get(autocast or "", None)
         self.net = net.to(self.device)
         self.is_bert = dnn.startswith("bert")
+        if self.device.type == "cuda" and self.dataset in ("cifar10", "imagenet", "mnist"):
+            torch.backends.cudnn.benchmark = True    # fixed input shapes: let cuDNN pick the fastest conv algorithms
         if pretrain:
             self.load_checkpoint(pretrain, model_only=True)
         broadcast_parameters(self.net, 0, self.world)
@@ -191,10 +193,11 @@ class Trainer:
         for _ in range(num_of_iters):
             self.adjust_learning_rate()
             t0 = time.perf_counter()
-            batch = self.prefetch.next()
+            batch = self.prefetch.next(defer=True)
             self.timers.add("io", time.perf_counter() - t0)
             loss, aux = self._forward_loss(batch)
             loss.backward()
+            self.prefetch.advance()              # stage the next batch while the GPU works through this one
             self._last_loss = loss.detach()
             self.loss_n += 1
             if self.train_iter % self.iters_per_epoch == self.iters_per_epoch - 1:
@@ -227,7 +230,8 @@ class Trainer:
         if self.graphed is not None and self.graphed.enabled:
             self.net.train()
             self.adjust_learning_rate()
-            self._last_loss = self.graphed.step(self.prefetch.next())
+            self._last_loss = self.graphed.step(self.prefetch.next(defer=True))
+            self.prefetch.advance()              # host-side staging of the next batch overlaps the replayed step
             self._bookkeep_iter()
             return
         self.optimizer.zero_grad()
