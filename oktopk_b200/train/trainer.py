@@ -74,8 +74,8 @@ class Trainer:
         self.autocast = {"bf16": torch.bfloat16, "fp16": torch.float16}.get(autocast or "", None)
         self.net = net.to(self.device)
         self.is_bert = dnn.startswith("bert")
-        if self.device.type == "cuda" and self.dataset in ("cifar10", "imagenet", "mnist"):
-            torch.backends.cudnn.benchmark = True    # fixed input shapes: let cuDNN pick the fastest conv algorithms
+        # (cudnn.benchmark is deliberately left off: its autotune passes empty the caching allocator, which makes the
+        #  next eager step -- the 1-in-32 exact-threshold flavour that is not graph-replayed -- re-cudaMalloc everything)
         if pretrain:
             self.load_checkpoint(pretrain, model_only=True)
         broadcast_parameters(self.net, 0, self.world)
