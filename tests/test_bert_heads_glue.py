@@ -104,7 +104,9 @@ def test_processors_read_tsv(tmp_path):
 def test_finetune_on_synthetic_task_beats_chance():
     tok = BertTokenizer.synthetic(3000)
     train, dev = glue.synthetic_examples(256, "mrpc", 0), glue.synthetic_examples(96, "mrpc", 1)
-    res = glue.finetune_and_score("mrpc", train, dev, CFG, tok, max_seq_length=24, epochs=12, lr=5e-4, batch_size=32,
+    import dataclasses
+    cfg = dataclasses.replace(CFG, num_hidden_layers=2)
+    res = glue.finetune_and_score("mrpc", train, dev, cfg, tok, max_seq_length=24, epochs=16, lr=5e-4, batch_size=32,
                                   device=torch.device("cpu"))
     assert set(res) == {"acc", "f1", "acc_and_f1"} and all(math.isfinite(v) for v in res.values())
     assert res["acc"] > 0.6, res
