@@ -126,6 +126,103 @@ class SyntheticWikipedia(Dataset):
         return ids[0], seg[0], mask[0], labels[0], nxt[0]
 
 
+class PTBText(Dataset):
+    """Penn Treebank from ``ptb.{train,valid,test}.txt`` (``VGG/ptb_reader.py``: whitespace tokens, ``<eos>`` per line,
+    vocabulary sorted by frequency) as ``num_steps`` windows of (input, shifted target)."""
+
+    def __init__(self, data_dir: str, split: str = "train", num_steps: int = 35, vocab: Optional[Dict[str, int]] = None):
+        import collections
+        import os
+
+        def read(path):
+            with open(path, "r", encoding="utf-8") as f:
+                return f.read().replace("\n", " <eos> ").split()
+        if vocab is None:
+            words = read(os.path.join(data_dir, "ptb.train.txt"))
+            cnt = collections.Counter(words)
+            vocab = {w: i for i, (w, _) in enumerate(sorted(cnt.items(), key=lambda kv: (-kv[1], kv[0])))}
+        self.vocab = vocab
+        unk = vocab.get("<unk>", 0)
+        toks = read(os.path.join(data_dir, "ptb.%s.txt" % split))
+        self.data = torch.tensor([vocab.get(w, unk) for w in toks], dtype=torch.long)
+        self.num_steps = num_steps
+        self.n = max((self.data.numel() - 1) // num_steps, 0)
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        s = i * self.num_steps
+        return self.data[s:s + self.num_steps], self.data[s + 1:s + 1 + self.num_steps]
+
+
+class AN4Manifest(Dataset):
+    """AN4-style speech corpus from a manifest (``wav_path,transcript_path`` per line -- the deepspeech.pytorch layout
+    the reference's missing ``audio_data/data_loader.py`` consumed): 16 kHz wav -> log-magnitude STFT
+    spectrogram (20 ms window, 10 ms stride => 161 bins), per-utterance normalisation, transcript -> label ids."""
+
+    def __init__(self, manifest: str, labels: str, sample_rate: int = 16000, window_size: float = 0.02,
+                 window_stride: float = 0.01, normalize: bool = True):
+        import os
+        self.items = []
+        base = os.path.dirname(os.path.abspath(manifest))
+        with open(manifest) as f:
+            for line in f:
+                line = line.strip()
+                if line:
+                    a, b = line.split(",")[:2]
+                    self.items.append((a if os.path.isabs(a) else os.path.join(base, a),
+                                       b if os.path.isabs(b) else os.path.join(base, b)))
+        self.labels_map = {c: i for i, c in enumerate(labels)}
+        self.sr, self.n_fft, self.hop = sample_rate, int(sample_rate * window_size), int(sample_rate * window_stride)
+        self.normalize = normalize
+
+    def __len__(self):
+        return len(self.items)
+
+    def spectrogram(self, wav_path: str) -> torch.Tensor:
+        from scipy.io import wavfile
+        sr, y = wavfile.read(wav_path)
+        y = torch.as_tensor(y.astype("float32"))
+        if y.dim() > 1:
+            y = y.mean(1)
+        if y.abs().max() > 1.5:
+            y = y / 32768.0
+        win = torch.hamming_window(self.n_fft, periodic=False)
+        spec = torch.stft(y, self.n_fft, self.hop, self.n_fft, window=win, return_complex=True).abs()
+        spec = torch.log1p(spec)
+        if self.normalize:
+            spec = (spec - spec.mean()) / (spec.std() + 1e-8)
+        return spec                                            # [n_fft // 2 + 1 = 161, frames]
+
+    def __getitem__(self, i):
+        wav, txt = self.items[i]
+        with open(txt, "r", encoding="utf-8") as f:
+            t = f.read().strip().upper()
+        target = torch.tensor([self.labels_map[c] for c in t if c in self.labels_map], dtype=torch.long)
+        return self.spectrogram(wav), target
+
+
+class ImageNetHDF5(Dataset):
+    """ImageNet packed in one HDF5 file (``VGG/datasets.py:8-36``): datasets ``<split>_img`` uint8 ``[N,H,W,3]`` and
+    ``<split>_labels``.  Needs ``h5py`` (not in this image: raises ImportError, callers fall back to synthetic)."""
+
+    def __init__(self, path: str, train: bool = True):
+        import h5py                                             # noqa: WPS433
+        self.f = h5py.File(path, "r")
+        k = "train" if train else "val"
+        self.img, self.lab = self.f[k + "_img"], self.f[k + "_labels"]
+        self.mean = torch.tensor([0.485, 0.456, 0.406]).view(3, 1, 1)
+        self.std = torch.tensor([0.229, 0.224, 0.225]).view(3, 1, 1)
+
+    def __len__(self):
+        return int(self.lab.shape[0])
+
+    def __getitem__(self, i):
+        x = torch.from_numpy(self.img[i]).permute(2, 0, 1).float() / 255.0
+        return (x - self.mean) / self.std, int(self.lab[i])
+
+
 def build_dataset(name: str, data_dir: Optional[str] = None, train: bool = True, seed: int = 0, **kw) -> Dataset:
     """Real data if it is already on disk under ``data_dir`` (never downloads), else synthetic."""
     name = name.lower()
@@ -139,6 +236,22 @@ def build_dataset(name: str, data_dir: Optional[str] = None, train: bool = True,
                 return torchvision.datasets.CIFAR10(data_dir, train=train, download=False, transform=tf)
             tf = T.Compose([T.ToTensor(), T.Normalize((0.1307,), (0.3081,))])
             return torchvision.datasets.MNIST(data_dir, train=train, download=False, transform=tf)
+        except Exception:  # noqa: BLE001 - fall back to synthetic
+            pass
+    if data_dir and name in ("ptb", "an4", "imagenet"):
+        import os
+        try:
+            if name == "ptb" and os.path.isfile(os.path.join(data_dir, "ptb.train.txt")):
+                return PTBText(data_dir, "train" if train else "valid", kw.get("num_steps", 35))
+            if name == "an4":
+                man = os.path.join(data_dir, "an4_train_manifest.csv" if train else "an4_val_manifest.csv")
+                if os.path.isfile(man):
+                    from ..models.deepspeech import AN4_LABELS
+                    return AN4Manifest(man, AN4_LABELS)
+            if name == "imagenet":
+                for cand in ("imagenet-shuffled.hdf5", "imagenet.hdf5"):
+                    if os.path.isfile(os.path.join(data_dir, cand)):
+                        return ImageNetHDF5(os.path.join(data_dir, cand), train)
         except Exception:  # noqa: BLE001 - fall back to synthetic
             pass
     if name == "cifar10":

@@ -123,3 +123,30 @@ def test_flops_counter_matches_known_models():
     assert params == 14_728_266 and 3.1e8 < macs < 3.2e8 and per["conv"] > 0.99 * 3.13e8
     s_macs, s_params = get_model_complexity_info(net, (3, 32, 32))
     assert s_macs.endswith("MMac") and s_params == "14.73 M"
+
+
+def test_ptb_and_an4_file_loaders(tmp_path):
+    """Real-data loaders (used when the files are on disk; synthetic otherwise): PTB text and an AN4-style manifest."""
+    import numpy as np
+    from scipy.io import wavfile
+    from oktopk_b200.models.deepspeech import AN4_LABELS
+    from oktopk_b200.train.data import AN4Manifest, PTBText, an4_collate, build_dataset
+    (tmp_path / "ptb.train.txt").write_text(" the cat sat on the mat \n the dog sat \n" * 30)
+    (tmp_path / "ptb.valid.txt").write_text(" the cat sat \n" * 10)
+    ds = build_dataset("ptb", str(tmp_path), train=True, num_steps=5)
+    assert isinstance(ds, PTBText) and ds.vocab["the"] == 0 and "<eos>" in ds.vocab
+    x, y = ds[0]
+    assert x.shape == (5,) and torch.equal(x[1:], y[:-1])
+    sr = 16000
+    for i, text in enumerate(["HELLO WORLD", "GO"]):
+        t = np.arange(int(sr * (0.5 + 0.3 * i))) / sr
+        wavfile.write(str(tmp_path / ("u%d.wav" % i)), sr, (0.3 * np.sin(2 * np.pi * 440 * (i + 1) * t) * 32767).astype(np.int16))
+        (tmp_path / ("u%d.txt" % i)).write_text(text)
+    (tmp_path / "an4_train_manifest.csv").write_text("u0.wav,u0.txt\nu1.wav,u1.txt\n")
+    an4 = build_dataset("an4", str(tmp_path), train=True)
+    assert isinstance(an4, AN4Manifest) and len(an4) == 2
+    spec, tgt = an4[0]
+    assert spec.shape[0] == 161 and spec.shape[1] == 51 and tgt.numel() == len("HELLO WORLD")
+    assert [AN4_LABELS[int(i)] for i in tgt] == list("HELLO WORLD")
+    inputs, targets, pct, sizes = an4_collate([an4[0], an4[1]])
+    assert inputs.shape[:3] == (2, 1, 161) and sizes.tolist() == [2, 11] or sizes.tolist() == [11, 2]
