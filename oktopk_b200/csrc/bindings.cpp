@@ -148,6 +148,7 @@ static void oktopk_run(uint64_t g, uint64_t res, uint64_t st, const std::vector<
     p.l_factor = (float)getf("l_factor", 1.012);
     p.g_low_cnt = getf("g_low_cnt", 0.0); p.g_high_cnt = getf("g_high_cnt", 1e30);
     p.g_inc = (float)getf("g_inc", 1.008); p.g_dec = (float)getf("g_dec", 1.008);
+    p.prefilter = (float)getf("prefilter", 0.8);
     p.timeout_ns = (unsigned long long)(getf("timeout_s", 0.0) * 1e9);
     if (geti("split_phases", 0)) {
         // ablation / debugging: one launch per phase instead of the single persistent kernel

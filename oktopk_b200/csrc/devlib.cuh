@@ -73,7 +73,7 @@ __device__ __forceinline__ int block_excl_scan(int v, int* s_w, int* total) {
 // magnitude bit pattern), grid-wide.  The per-pass digit histogram is built in shared memory,
 // merged into st->hist, and block 0 picks the digit; state travels in st->sel_prefix/sel_krem.
 // ------------------------------------------------------------------------------------------
-struct Seg { const float* ptr; int count; };
+struct Seg { const float* ptr; int count; const int* idx; };   // idx != nullptr: the values are ptr[idx[i]]
 
 __device__ __forceinline__ void digit_of_pass(int pass, int& shift, int& nbits) {
     shift = (pass == 0) ? 20 : (pass == 1 ? 10 : 0);
@@ -152,8 +152,10 @@ static __device__ float grid_kth_abs(const Seg* segs, int nseg, bool remote, uin
             for (int s = 0; s < nseg; ++s) {
                 const float* ptr = segs[s].ptr;
                 const int cnt = segs[s].count;
+                const int* idx = segs[s].idx;
                 for (int i = gtid; i < cnt; i += gthreads) {
-                    float v = remote ? ld_peer_f32(ptr + i) : __ldcg(ptr + i);
+                    const int j = idx ? __ldcg(idx + i) : i;
+                    float v = remote ? ld_peer_f32(ptr + j) : __ldcg(ptr + j);
                     hist_add(s_hist, v, pass, prefix);
                 }
             }

@@ -91,24 +91,87 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
                 }
             }
         };
-        for (int v = gtid; v < n4; v += gthreads) {
-            float4 a = ld_stream_f4(g4 + v);
-            float4 r = ld_stream_f4(r4 + v);
-            a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
-            st_stream_f4(r4 + v, a);
-            visit(a.x); visit(a.y); visit(a.z); visit(a.w);
+        // Exact iterations: instead of histogramming all n magnitudes (shared-memory atomics on a handful of hot
+        // exponent bins), only the elements above a cut derived from the carried threshold become candidates for the
+        // radix select -- a few k of them.  The k-th largest of the candidates IS the k-th largest overall as long as
+        // at least k elements pass the cut; otherwise (first call, or the gradient scale collapsed) fall back to the
+        // full three-pass select.
+        const float cut = (p.exact_local && thr0 > 0.f) ? thr0 * p.prefilter : -1.f;
+        const bool prefilter = cut > 0.f;
+        constexpr int kLocTile = 4;
+        for (int base = blockIdx.x * kThreads * kLocTile; base < n4; base += gridDim.x * kThreads * kLocTile) {
+            float4 a[kLocTile], r[kLocTile];
+            bool in[kLocTile];
+#pragma unroll
+            for (int u = 0; u < kLocTile; ++u) {
+                const int v = base + u * kThreads + tid;
+                in[u] = v < n4;
+                if (in[u]) { a[u] = ld_stream_f4(g4 + v); r[u] = ld_stream_f4(r4 + v); }
+                else { a[u] = make_float4(0.f, 0.f, 0.f, 0.f); r[u] = a[u]; }
+            }
+#pragma unroll
+            for (int u = 0; u < kLocTile; ++u) {
+                const int v = base + u * kThreads + tid;
+                a[u].x += r[u].x; a[u].y += r[u].y; a[u].z += r[u].z; a[u].w += r[u].w;
+                if (in[u]) st_stream_f4(r4 + v, a[u]);
+                const float xs[4] = {a[u].x, a[u].y, a[u].z, a[u].w};
+                if (!prefilter) {
+                    if (in[u]) { visit(xs[0]); visit(xs[1]); visit(xs[2]); visit(xs[3]); }
+                    continue;
+                }
+                unsigned bits = 0u;
+                int tot = 0;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const bool pd = in[u] && fabsf(xs[c]) > cut;
+                    if (pd) bits |= 1u << c;
+                    tot += __popc(__ballot_sync(0xffffffffu, pd));
+                }
+                if (tot == 0) continue;
+                int run = 0;
+                if (lane == 0) run = atomicAdd(&st->cand_cursor, tot);
+                run = __shfl_sync(0xffffffffu, run, 0);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const bool pd = (bits >> c) & 1u;
+                    const unsigned m = __ballot_sync(0xffffffffu, pd);
+                    if (pd) {
+                        const int pos = run + __popc(m & ((1u << lane) - 1u));
+                        if (pos < p.ccap) p.cand[pos] = 4 * v + c;
+                    }
+                    run += __popc(m);
+                }
+            }
         }
         if (blockIdx.x == 0) {
             for (int i = n4 * 4 + tid; i < n; i += kThreads) {
                 float a = p.g[i] + p.res[i];
                 p.res[i] = a;
-                visit(a);
+                if (prefilter) {
+                    if (fabsf(a) > cut) { int pos = atomicAdd(&st->cand_cursor, 1); if (pos < p.ccap) p.cand[pos] = i; }
+                } else {
+                    visit(a);
+                }
             }
         }
         if (p.exact_local) {
-            hist_flush(st, s_hist);
-            Seg seg{p.res, n};
-            float thr = grid_kth_abs(&seg, 1, false, (uint32_t)p.k, st, s_hist, s_w, /*first_pass=*/1);
+            float thr;
+            bool done = false;
+            if (prefilter) {
+                grid_sync(&st->bar);
+                const int ncand = *reinterpret_cast<volatile int*>(&st->cand_cursor);
+                if (ncand >= p.k && ncand <= p.ccap) {
+                    Seg seg{p.res, ncand, p.cand};
+                    thr = grid_kth_abs(&seg, 1, false, (uint32_t)p.k, st, s_hist, s_w, 0);
+                    done = true;
+                }
+            }
+            if (!done) {
+                if (!prefilter) hist_flush(st, s_hist);
+                Seg seg{p.res, n, nullptr};
+                thr = grid_kth_abs(&seg, 1, false, (uint32_t)p.k, st, s_hist, s_w, /*first_pass=*/prefilter ? 0 : 1);
+            }
+            if (blockIdx.x == 0 && tid == 0) { st->local_thr_used = thr; st->cand_cursor = 0; }
             if (blockIdx.x == 0 && tid == 0) st->local_thr_used = thr;
         } else {
 #pragma unroll
@@ -341,6 +404,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const bool pred = in[u] && fabsf(xs[c]) > thr_sel;
+                    // TopkDSA zeroes the residual at the exact top-k INCLUDING the k-th element itself, which the
+                    // strict '>' select does not send (reference quirk): a rare, direct store
+                    if (p.residual_mode == RES_LOCAL_GE && in[u] && xs[c] != 0.f && fabsf(xs[c]) == thr_sel)
+                        p.res[4 * (base + u * kThreads + tid) + c] = 0.f;
                     const unsigned m = __ballot_sync(0xffffffffu, pred);
                     msk[u * 4 + c] = m;
                     tot += __popc(m);
@@ -429,11 +496,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
             }
             emit(i, a, in);
         }
-        if (p.residual_mode == RES_LOCAL_GE) {
-            // TopkDSA zeroes the residual at the exact top-k, i.e. including the k-th element itself
-            // which the strict '>' select above does not send (reference quirk).
-            for (int i = gtid; i < n; i += gthreads) {
-                float x = __ldcg(p.res + i);
+        if (p.residual_mode == RES_LOCAL_GE && blockIdx.x == 0 && (n & 3)) {      // scalar tail of the same rule
+            for (int i = n4 * 4 + tid; i < n; i += kThreads) {
+                float x = p.res[i];
                 if (x != 0.f && fabsf(x) == thr_sel) p.res[i] = 0.f;
             }
         }
@@ -653,7 +718,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
         float gsel = 0.f;
         if (p.global_mode == GLB_EXACT_TOPK) {
             Seg segs[OKT_MAXP];
-            for (int s = 0; s < P; ++s) { segs[s].ptr = gat_val(p.peers[s], p.L, par); segs[s].count = s_cnt[s]; }
+            for (int s = 0; s < P; ++s) { segs[s].ptr = gat_val(p.peers[s], p.L, par); segs[s].count = s_cnt[s]; segs[s].idx = nullptr; }
             const uint32_t kk = (uint32_t)min(T, p.k);
             gsel = (kk > 0) ? grid_kth_abs(segs, P, true, kk, st, s_hist, s_w, 0) : 0.f;
             if (blockIdx.x == 0 && tid == 0) st->global_thr = gsel;
@@ -706,7 +771,7 @@ __global__ void __launch_bounds__(kThreads, 2) kth_abs_kernel(const float* x, in
     __shared__ int s_w[kWarps + 1];
     for (int b = threadIdx.x; b < kHistBins; b += kThreads) s_hist[b] = 0;
     __syncthreads();
-    Seg seg{x, n};
+    Seg seg{x, n, nullptr};
     float t = grid_kth_abs(&seg, 1, false, (uint32_t)k, st, s_hist, s_w, 0);
     if (blockIdx.x == 0 && threadIdx.x == 0) *out = t;
 }

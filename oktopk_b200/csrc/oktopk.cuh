@@ -110,6 +110,7 @@ struct OktParams {
     int* cand;           // local scratch: region-local indices that received a contribution (capacity ccap)
     int ccap;
     int cand_mode;       // 1: first-touch candidate list (low density), 0: region scan (high density)
+    float prefilter;     // exact iterations: radix-select only elements above prefilter * carried threshold (0 = all)
     char* peers[OKT_MAXP];   // every rank's symmetric block as mapped into this process
     SymmLayout L;
     int n, P, rank, k;

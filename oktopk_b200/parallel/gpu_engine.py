@@ -88,7 +88,8 @@ class CudaBucketEngine:
         self.dense_epoch_ptr = C.dev_alloc_zero(8 * self.dense_grid)
         self.residual = torch.zeros(self.n, dtype=torch.float32, device=self.device)
         # first-touch candidate list of the reduce phase: at most one entry per pulled (idx,val) pair
-        self.ccap = int(min(_round_up(self.n, 32), self.P * self.cap))
+        # (also holds the pre-filtered candidates of the exact-threshold radix select: a few k entries)
+        self.ccap = int(min(_round_up(self.n, 32), max(self.P * self.cap, 32 * kmax + chunk)))
         self.cand = torch.zeros(self.ccap, dtype=torch.int32, device=self.device)
         self.host = SparseState(self.n, self.P)          # counter + (lazily refreshed) mirrors
         self._write_edges(self.host.region_offsets + [self.n])
