@@ -32,6 +32,171 @@ def _unavailable(why: str) -> dict:
     return {"impl": "reference", "unavailable": why}
 
 
+def run_reference_bert(args, MODELS) -> dict:
+    """The reference's BERT program: its stage modules (``models/bert/depth=4``: 12 layers as 4 modules run back to back on
+    every rank, untied decoder), its ``transformers.modeling`` layers, its ``BertAdam(..., density, compressor)`` with the
+    embedded synchronous ``AllReducer`` (``optimization.py:68-227`` -> ``allreducer.py:347``), driven by the body of
+    ``StageRuntime.run_training_loop_with_flushes`` (``runtime.py:842-900``: forward, loss = CE(MLM)+CE(NSP) as in
+    ``runtime.py:585-596``, backward, ``optimizer.step()``, ``zero_grad()``).  apex / amp_C / boto3 are import-only
+    dependencies of that code (never called): ``baseline/shims`` provides inert stand-ins, so its ``BertLayerNorm`` takes
+    its own non-apex branch."""
+    import importlib
+    import torch
+    cpu_dry = os.environ.get("OKTOPK_REF_CPU_TEST", "0") == "1"
+    if not torch.cuda.is_available() and not cpu_dry:
+        return _unavailable("no CUDA device")
+    bert_dir = os.path.join(TREE, "BERT", "bert")
+    sys.path.insert(0, os.path.join(TREE, "BERT"))
+    sys.path.insert(0, bert_dir)
+    sys.path.insert(0, SHIMS)
+    os.chdir(bert_dir)
+    if cpu_dry:                                                  # test scaffold only (no GPU in the authoring box)
+        torch.cuda.synchronize = lambda *a, **k: None
+        torch.Tensor.cuda = lambda self, *a, **k: self
+    import warnings
+    warnings.filterwarnings("ignore")
+    import logging
+    logging.getLogger().setLevel(logging.WARNING)
+    import io
+    import contextlib
+    from mpi4py import MPI
+    comm = MPI.COMM_WORLD
+    rank, size = comm.rank, comm.size
+    dev = torch.device("cpu")
+    if torch.cuda.is_available():
+        local = int(os.environ.get("LOCAL_RANK", rank))
+        torch.cuda.set_device(local % torch.cuda.device_count())
+        dev = torch.device("cuda", torch.cuda.current_device())
+    quiet = io.StringIO()
+    with contextlib.redirect_stdout(quiet):
+        from transformers.modeling import BertConfig          # the reference's local package, not HuggingFace's
+        from transformers.optimization import BertAdam
+        import settings
+    settings.logger.setLevel(logging.WARNING)
+    dnn, dataset, bs0, lr, _preset = MODELS[args.model]
+    bs = args.batch_size or bs0
+    seq = args.seq_len
+    config = BertConfig.from_json_file(os.path.join(bert_dir, "configs", "bert_config_bert-base-uncased.json"))
+    layers = int(os.environ.get("OKTOPK_REF_BERT_LAYERS", "12"))   # main_bert.py:806-812: 'bert12' -> 12 layers
+    config.num_hidden_layers = layers
+    torch.manual_seed(0)                                         # same init on every rank
+    module = importlib.import_module("models.bert.depth=4")
+    criterion = torch.nn.CrossEntropyLoss(ignore_index=-1)      # main_bert.py:815
+    spec = module.model(config, criterion)
+    stages = [ctor().to(dev) for ctor, _i, _o in spec[:-1]]
+    names = [(i, o) for _c, i, o in spec[:-1]]
+    named, params = [], []
+    for si, st in enumerate(stages):
+        for n, p in st.named_parameters():
+            named.append(("s%d.%s" % (si, n), p))
+    no_decay = ["bias", "gamma", "beta", "LayerNorm"]             # main_bert.py:972-985
+    groups = [{"params": [p for n, p in named if not any(nd in n for nd in no_decay)], "weight_decay": 0.01},
+              {"params": [p for n, p in named if any(nd in n for nd in no_decay)], "weight_decay": 0.0}]
+    with contextlib.redirect_stdout(quiet):
+        optimizer = BertAdam(groups, lr=lr, warmup=0.1, t_total=100000, density=args.density,
+                             compressor=args.compressor, rank=rank)
+    for st in stages:
+        st.train()
+    vocab = config.vocab_size
+
+    def make_batch(i):
+        g = torch.Generator().manual_seed(4321 + 977 * i + rank)
+        ids = torch.randint(1000, vocab, (bs, seq), generator=g)
+        seg = (torch.arange(seq).unsqueeze(0) >= torch.randint(seq // 4, 3 * seq // 4, (bs, 1), generator=g)).long()
+        lens = torch.randint(seq // 2, seq + 1, (bs, 1), generator=g)
+        mask = (torch.arange(seq).unsqueeze(0) < lens).long()
+        sel = (torch.rand(bs, seq, generator=g) < 0.15) & mask.bool()
+        labels = torch.where(sel, ids, torch.full_like(ids, -1))
+        ids = torch.where(sel, torch.full_like(ids, 103), ids) * mask
+        nxt = torch.randint(0, 2, (bs,), generator=g)
+        return (ids, mask, seg, labels, nxt)
+
+    def fwd(batch):
+        ids, mask, seg, labels, nxt = batch
+        t = {"input0": ids, "input1": seg,
+             "input2": (1.0 - mask.unsqueeze(1).unsqueeze(2).to(torch.float32)) * -10000.0}   # main_bert.py:629-631
+        for st, (ins, outs) in zip(stages, names):
+            res = st(*[t[n] for n in ins])
+            if len(outs) == 1:
+                t[outs[0]] = res
+            else:
+                for n, r in zip(outs, res):
+                    t[n] = r
+        scores, nsp = t[names[-1][1][0]]
+        return criterion(scores.view(-1, vocab), labels.view(-1)) + criterion(nsp.view(-1, 2), nxt.view(-1))
+
+    pinned = torch.cuda.is_available()
+    pool_host = [make_batch(i) for i in range(8)]
+    if pinned:
+        pool_host = [tuple(t.pin_memory() for t in b) for b in pool_host]
+    pool_dev = [tuple(t.to(dev) for t in b) for b in pool_host[:4]]
+
+    def step(batch):
+        loss = fwd(batch)
+        loss.backward()
+        with contextlib.redirect_stdout(quiet):                  # the reference prints "allreducer time" every step
+            optimizer.step()
+        optimizer.zero_grad()
+        return loss
+
+    def sync_all():
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        comm.Barrier()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+
+    if size == 1 and args.compressor != "none":
+        return _unavailable("reference BERT Ok-Topk cannot run on one rank (region boundaries of a (P-1)-element array, "
+                            "BERT/bert/allreducer.py:385-396) and the BERT program has no dense warm-up phase to time")
+    for i in range(args.warmup):
+        step(pool_dev[i % len(pool_dev)])
+    sync_all()
+
+    def timed(fn_batch, read_loss):
+        import numpy as np
+        if torch.cuda.is_available():
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            loss = step(fn_batch(i))
+            if read_loss:
+                _ = float(loss.detach())
+        if torch.cuda.is_available():
+            e1.record()
+        sync_all()
+        wall = (time.perf_counter() - t0) * 1e3
+        ms = e0.elapsed_time(e1) if torch.cuda.is_available() else wall
+        if size > 1:
+            allv, mine = np.zeros(size, dtype=np.float64), np.zeros(size, dtype=np.float64)
+            mine[rank] = ms
+            comm.Allreduce(mine, allv, MPI.SUM)
+            ms = float(allv.max())
+        return ms, wall
+
+    ms_total, _ = timed(lambda i: pool_dev[i % len(pool_dev)], False)
+    h2d = sum(t.numel() * t.element_size() for t in pool_host[0])
+    e2e_ms, wall = timed(lambda i: tuple(t.to(dev, non_blocking=True) for t in pool_host[i % len(pool_host)]), True)
+    n_params = sum(p.numel() for _n, p in named)
+    out = {
+        "metric": "train_samples_per_sec_%s_oktopk_density%g" % (args.model, args.density),
+        "value": bs * size * args.steps / (ms_total * 1e-3), "unit": "samples/s", "n_gpus": size, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "impl": "reference",
+        "config": {"model": dnn, "dataset_shape": dataset, "global_batch": bs * size, "per_gpu_batch": bs, "seq_len": seq,
+                   "parallelism": "dp%d" % size, "compressor": args.compressor, "density": args.density, "params": n_params,
+                   "layers": layers, "reference_dense_warmup_steps_untimed": 0, "timed_phase": "sparse (the BERT program "
+                   "has no dense warm-up)", "comm": "mpi4py shim over torch.distributed gloo (host NumPy buffers, as in the "
+                   "reference)", "import_only_shims": ["apex", "amp_C", "boto3"]},
+        "e2e": {"value": bs * size * args.steps / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": wall / args.steps,
+                "steps": args.steps},
+        "gpu_launches": 0,
+    }
+    return out if rank == 0 else None
+
+
 def run_reference(args, MODELS) -> dict:
     if not os.path.isdir(os.path.join(TREE, "VGG")):
         try:
@@ -40,8 +205,7 @@ def run_reference(args, MODELS) -> dict:
         except Exception as e:  # noqa: BLE001
             return _unavailable("reference tree missing and install failed: %r" % (e,))
     if args.model == "bert":
-        return _unavailable("reference BERT imports apex/amp_C CUDA extensions (optimization.py:24-34) that are not "
-                            "installable offline; VGG-16 and LSTM-AN4 arms are available")
+        return run_reference_bert(args, MODELS)
     import torch
     cpu_dry = os.environ.get("OKTOPK_REF_CPU_TEST", "0") == "1"
     if not torch.cuda.is_available() and not cpu_dry:
