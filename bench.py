@@ -227,7 +227,7 @@ def run_ours(args) -> dict:
                                                         "why_disabled": tr.graphed.why_disabled}),
         "final_loss": tr.last_loss(),
         "comm": {k: {kk: v[kk] for kk in ("mode", "local_count", "global_count", "volume_elems", "overflow_send",
-                                          "overflow_gather") if kk in v} for k, v in stats.items()},
+                                          "overflow_gather", "fault", "phase_us") if kk in v} for k, v in stats.items()},
     }
     tr.close()
     okt.shutdown()

@@ -71,7 +71,7 @@ class OkTopkConfig:
     pull_mode: str = "tma"              # 'tma' (cp.async.bulk of remote chunks) | 'ldg' (128-bit peer loads)
     overlap: bool = True                # launch a bucket's exchange as soon as its last grad lands
     gselect_mode: str = "auto"          # global selection over the reduced region: 'list' | 'scan' | 'auto' (density <= 0.5 % -> list)
-    peer_timeout_s: float = 20.0        # bound of every cross-GPU flag wait inside the kernels (0 = wait forever)
+    peer_timeout_s: float = 60.0        # bound of every cross-GPU flag wait inside the kernels (0 = wait forever)
 
     def k_for(self, numel: int, density: Optional[float] = None) -> int:
         d = self.density if density is None else density
