@@ -41,18 +41,26 @@ MODELS = {
 class ClockSampler:
     """nvidia-smi clocks/throttle-reason sampling during the timed region (B200_PROFILING.md recipe)."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.idx = gpu_index
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.t_mark = None
+
+    def mark(self):
+        """Start of the timed region: only samples taken after this instant are reported.  (The sampler process itself
+        is started BEFORE the warm-up: nvidia-smi's NVML initialisation takes a driver-wide lock for ~0.2 s, which must not
+        land inside the timed steps.)"""
+        import datetime
+        self.t_mark = datetime.datetime.now()
 
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:  # noqa: BLE001
             self.p = None
@@ -70,10 +78,18 @@ class ClockSampler:
         self.f.seek(0)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        import datetime
         for line in self.f.read().splitlines():
             c = [x.strip() for x in line.split(",")]
             if len(c) < 9:
                 continue
+            if self.t_mark is not None:
+                try:
+                    ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f")
+                    if ts < self.t_mark:
+                        continue
+                except ValueError:
+                    pass
             try:
                 sm.append(float(c[1]))
                 mx.append(float(c[2]))
@@ -161,12 +177,13 @@ def run_ours(args) -> dict:
         return loss
 
     dense_warm = int(cfg.warmup_iters) if args.compressor != "none" else 0
-    for i in range(dense_warm + args.warmup):
-        step_resident(i)
-    sync_all()
     sampler = ClockSampler(torch.cuda.current_device())
     if w.rank == 0:
         sampler.start()
+    for i in range(dense_warm + args.warmup):
+        step_resident(i)
+    sync_all()
+    sampler.mark()
     launches0 = ext.LAUNCH_COUNT["total"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
