@@ -60,7 +60,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:  # noqa: BLE001
             self.p = None
@@ -109,7 +109,7 @@ class ClockSampler:
 def parse_args(argv=None):
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=100)
+    p.add_argument("--steps", type=int, default=200)
     p.add_argument("--warmup", type=int, default=20)
     p.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
     p.add_argument("--model", type=str, default=os.environ.get("OKTOPK_BENCH_MODEL", "vgg16"), choices=sorted(MODELS))
