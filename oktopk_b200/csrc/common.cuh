@@ -20,6 +20,15 @@
 namespace okt {
 
 // ----------------------------------------------------------------------------------------
+// timers
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// ----------------------------------------------------------------------------------------
 // memory-model primitives
 // ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void st_release_sys_u64(uint64_t* p, uint64_t v) {
@@ -54,11 +63,6 @@ __device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned 
 __device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
 
 // Failure detection on the device: every cross-GPU spin is bounded.  When a peer does not show up within
 // `timeout_ns` the waiter records a fault code in *fault (device memory, read lazily by the host) and gives up,
@@ -162,16 +166,28 @@ __device__ __forceinline__ void mbar_fence_init() {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Intra-SM wait (TMA completion / ring-stage hand-over).  These can only stall on a programming error, so the spin is
+// bounded: after ~4 s the kernel traps (a reported launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const unsigned long long t0 = globaltimer_ns();
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 4095u) == 0 && globaltimer_ns() - t0 > 4000000000ULL) __trap();
+    }
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // bytes: multiple of 16; src/dst 16-byte aligned. src may be a peer GPU's memory.
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {

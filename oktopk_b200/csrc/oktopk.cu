@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
     __shared__ int s_misc[OKT_MAXP * 2 + 4];
     __shared__ __align__(128) PullSmem s_pull;
     __shared__ __align__(8) uint64_t s_pk_bar[kPackStages];
+    __shared__ __align__(8) uint64_t s_pk_empty[kPackStages];
     __shared__ __align__(8) uint64_t s_sc_bar[kScanStages];
     extern __shared__ __align__(128) float4 dyn_pk[];       // TMA ring of the streaming pass (kPackSmemBytes)
 
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
     if (tid == 0) {
         mbar_init(&s_pull.bar[0], 1);
         mbar_init(&s_pull.bar[1], 1);
-        for (int q = 0; q < kPackStages; ++q) mbar_init(&s_pk_bar[q], 1);
+        for (int q = 0; q < kPackStages; ++q) { mbar_init(&s_pk_bar[q], 1); mbar_init(&s_pk_empty[q], kWarps); }
         for (int q = 0; q < kScanStages; ++q) mbar_init(&s_sc_bar[q], 1);
         mbar_fence_init();
     }
@@ -369,8 +370,13 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
         if (tid == 0)
             for (int j = 0; j < min(nmine, kPackStages - 1); ++j) arm(j);
         for (int j = 0; j < nmine; ++j) {
-            __syncthreads();                                            // stage (j-1) % kPackStages is drained: re-arm it
-            if (tid == 0 && j + kPackStages - 1 < nmine) arm(j + kPackStages - 1);
+            // Producer (thread 0): re-arm the stage tile j-1 used, once all kWarps warps have released it (per-stage
+            // "empty" mbarrier; no block-wide barrier per tile, so a warp waiting for its slot reservation does not
+            // hold up the other 15 -- they may run up to kPackStages-1 tiles ahead).
+            if (tid == 0 && j + kPackStages - 1 < nmine) {
+                if (j >= 1) mbar_wait(&s_pk_empty[(j - 1) % kPackStages], (uint32_t)((j - 1) / kPackStages) & 1u);
+                arm(j + kPackStages - 1);
+            }
             const int stg = j % kPackStages;
             mbar_wait(&s_pk_bar[stg], (uint32_t)(j / kPackStages) & 1u);
             const int base = (blockIdx.x + j * G) * kTileV;
@@ -391,6 +397,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
                     st_stream_f4(g4 + v, make_float4(0.f, 0.f, 0.f, 0.f));
                 }
             }
+            __syncwarp();                                               // the warp's part of the tile is in registers:
+            if (lane == 0) mbar_arrive(&s_pk_empty[stg]);               // release the stage (1 of kWarps arrivals)
             // ---- selection: one slot reservation per (warp, trip, destination) ------------------------------
             // 16 element flags per lane -> 16 ballots; the warp's trip covers 4 windows of 128 consecutive elements,
             // which (regions being contiguous ranges) almost always belong to ONE destination, so the append costs

@@ -167,3 +167,47 @@ def test_distributed_optimizer_two_gpus_replicas_stay_identical(compressor):
     assert r[0][2] > 1
     assert r[0][1] == r[1][1], "replicas diverged: %r vs %r" % (r[0][1], r[1][1])
     assert r[0][0][-1] < r[0][0][0]
+
+
+def _fault_worker(rank, P):
+    """Fault injection: rank 1 'dies' (never enters the second reduction).  Rank 0 must not hang: its bounded wait
+    records a fault code and ``check_fault`` raises."""
+    import time
+    from oktopk_b200.config import OkTopkConfig
+    from oktopk_b200.parallel.gpu_engine import CudaBucketEngine, PeerTimeoutError
+    from oktopk_b200.parallel.world import World
+    w = World()
+    cfg = OkTopkConfig(density=0.01, peer_timeout_s=1.5, slot_factor=64, gather_factor=64)
+    eng = CudaBucketEngine(200_000, cfg, w, name="t")
+    eng.grad.copy_(_grad(0, rank, 200_000).cuda())
+    eng.reduce("oktopk")
+    torch.cuda.synchronize()
+    eng.check_fault()                                    # healthy round: no fault
+    w.barrier()
+    outcome = "skipped"
+    if rank == 0:
+        eng.grad.copy_(_grad(1, rank, 200_000).cuda())
+        t0 = time.time()
+        eng.reduce("oktopk")
+        torch.cuda.synchronize()                         # returns: the kernel gave up waiting instead of hanging
+        dt = time.time() - t0
+        try:
+            eng.check_fault()
+            outcome = "no-fault"
+        except PeerTimeoutError as e:
+            outcome = "fault:%s:%.1f" % (str(e)[:40], dt)
+        eng.clear_fault()
+        torch.cuda.synchronize()
+        assert eng.stats()["fault"] == 0
+    else:
+        time.sleep(4.0)
+    w.barrier()
+    eng.close()
+    return outcome
+
+
+def test_peer_timeout_is_detected_not_hung():
+    got = run_distributed(_fault_worker, 2, (), backend="nccl", timeout=120)
+    assert got[0].startswith("fault:"), got
+    assert float(got[0].rsplit(":", 1)[1]) < 20.0
+    assert got[1] == "skipped"
