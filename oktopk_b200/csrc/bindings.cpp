@@ -50,6 +50,9 @@ static uint64_t dev_alloc_zero(size_t nbytes) {
     ck(cudaMemset(p, 0, nbytes), "cudaMemset");
     return (uint64_t)p;
 }
+static void dev_free(uint64_t p) {
+    if (p) ck(cudaFree(P_<void>(p)), "cudaFree");
+}
 static void memset_async(uint64_t p, int value, size_t nbytes, uint64_t stream) {
     ck(cudaMemsetAsync(P_<void>(p), value, nbytes, S_(stream)), "cudaMemsetAsync");
 }
@@ -226,6 +229,7 @@ PYBIND11_MODULE(_C, m) {
     m.def("symm_close", &symm_close);
     m.def("symm_free", &symm_free);
     m.def("dev_alloc_zero", &dev_alloc_zero);
+    m.def("dev_free", &dev_free);
     m.def("memset_async", &memset_async);
     m.def("can_access_peer", &can_access_peer);
     m.def("state_bytes", &state_bytes);

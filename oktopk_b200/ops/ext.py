@@ -49,7 +49,7 @@ def load(build_if_missing: bool = True):
             _b.build()
         _C = _CountingModule(importlib.import_module("oktopk_b200._C"))
         _ERR = None
-    except BaseException as e:  # noqa: BLE001
+    except Exception as e:  # noqa: BLE001
         _ERR = e
         _C = None
     return _C

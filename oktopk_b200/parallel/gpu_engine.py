@@ -241,4 +241,16 @@ class CudaBucketEngine:
         self._write_edges(edges, sd["local_thr"], sd["global_thr"])
 
     def close(self) -> None:
-        self.block.close()
+        """Release the symmetric block (collective: every rank must call it) and the local device state."""
+        if getattr(self, "_closed", False):
+            return
+        self._closed = True
+        self.block.close()                       # synchronises the device and the peer group first
+        for attr in ("state_ptr", "dense_epoch_ptr"):
+            ptr = getattr(self, attr, 0)
+            if ptr:
+                try:
+                    self.C.dev_free(ptr)
+                except Exception:  # noqa: BLE001 - teardown must not raise
+                    pass
+                setattr(self, attr, 0)
