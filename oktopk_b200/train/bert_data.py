@@ -171,3 +171,185 @@ def synthetic_corpus(n_docs: int = 64, sents: int = 8, words: int = 12, seed: in
 def extended_attention_mask(input_mask: torch.Tensor) -> torch.Tensor:
     """``(1 - mask) * -10000`` broadcast to ``[B,1,1,S]`` (``main_bert.py:616-639``)."""
     return (1.0 - input_mask[:, None, None, :].to(torch.float32)) * -10000.0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Pre-created training instances, stored as partitions (capability parity with ``BERT/bert/sources.py:30-255``
+# ``TokenInstance`` / ``PretrainingDataCreator`` / ``GenericPretrainingDataCreator`` / ``WikiPretrainingDataCreator`` and
+# ``BERT/bert/dataset.py:93-227`` ``BERTDatasetPartitioned``).  Documents are tokenised ONCE, packed into sentence-pair
+# instances of ~``max_seq_length`` tokens (BERT's original recipe: segments A/B split at a sentence boundary, B replaced by
+# a random document's text half of the time), duplicated ``dupe_factor`` times with different packings, and saved as
+# shards; the dataset then only masks on the fly.  Storage is ``torch.save`` of plain lists (not pickled Python objects).
+# ------------------------------------------------------------------------------------------------------------------
+@dataclass
+class TokenInstance:
+    tokens_a: List[str]
+    tokens_b: List[str]
+    is_next: int                      # 0 = B continues A, 1 = B is random (the reference's convention, sources.py:34)
+
+    def get_values(self):
+        return self.tokens_a, self.tokens_b, self.is_next
+
+
+class PretrainingDataCreator:
+    """``documents``: list of documents, each a list of sentences (strings)."""
+
+    def __init__(self, documents: Sequence[Sequence[str]], tokenizer: BertTokenizer, max_seq_length: int = 128,
+                 dupe_factor: int = 5, small_seq_prob: float = 0.1, seed: int = 0):
+        self.max_seq_length, self.dupe_factor, self.small_seq_prob = max_seq_length, dupe_factor, small_seq_prob
+        gen = torch.Generator().manual_seed(seed)
+        docs = [[tokenizer.tokenize(s) for s in d if s.strip()] for d in documents]
+        docs = [[s for s in d if s] for d in docs]
+        self._docs = [d for d in docs if len(d) >= 2]
+        self.instances: List[TokenInstance] = []
+        for _ in range(dupe_factor):
+            for di in range(len(self._docs)):
+                self.instances.extend(self._create(di, gen))
+        perm = torch.randperm(len(self.instances), generator=gen).tolist()
+        self.instances = [self.instances[i] for i in perm]
+        self._docs = None
+
+    @classmethod
+    def from_corpus(cls, path: str, tokenizer: BertTokenizer, sep: Optional[str] = None, **kw) -> "PretrainingDataCreator":
+        """``sep=None``: blank-line separated documents, one sentence per line (the ``BERTDataset`` format);
+        ``sep='<sep>'``: one document per line with ``<sep>``-joined sentences (``sources.py:55-63``)."""
+        docs, cur = [], []
+        with open(path, encoding="utf-8") as f:
+            for line in f:
+                line = line.rstrip("\n")
+                if sep is not None:
+                    parts = [p for p in line.split(sep) if p.strip()]
+                    if len(parts) > 3:
+                        docs.append(parts)
+                elif line.strip() == "":
+                    if cur:
+                        docs.append(cur)
+                    cur = []
+                else:
+                    cur.append(line)
+        if cur:
+            docs.append(cur)
+        return cls(docs, tokenizer, **kw)
+
+    def __len__(self) -> int:
+        return len(self.instances)
+
+    def _rand(self, gen, lo: int, hi: int) -> int:
+        return int(torch.randint(lo, hi + 1, (1,), generator=gen))
+
+    def _create(self, di: int, gen) -> List[TokenInstance]:
+        doc = self._docs[di]
+        max_tokens = self.max_seq_length - 3                       # [CLS] + 2 x [SEP]
+        target = max_tokens
+        if float(torch.rand(1, generator=gen)) < self.small_seq_prob:
+            target = self._rand(gen, 5, max_tokens)
+        out, chunk, length, i = [], [], 0, 0
+        while i < len(doc):
+            chunk.append(doc[i])
+            length += len(doc[i])
+            if i == len(doc) - 1 or length >= target:
+                if chunk:
+                    a_end = 1 if len(chunk) < 2 else self._rand(gen, 1, len(chunk) - 1)
+                    a = [t for s in chunk[:a_end] for t in s]
+                    is_random = len(chunk) == 1 or float(torch.rand(1, generator=gen)) < 0.5
+                    if is_random and len(self._docs) > 1:
+                        rd = di
+                        for _ in range(10):
+                            rd = self._rand(gen, 0, len(self._docs) - 1)
+                            if rd != di:
+                                break
+                        rdoc = self._docs[rd]
+                        start = self._rand(gen, 0, len(rdoc) - 1)
+                        b, budget = [], target - len(a)
+                        for s in rdoc[start:]:
+                            b.extend(s)
+                            if len(b) >= budget:
+                                break
+                        i -= len(chunk) - a_end                    # the unused sentences go back (no text is wasted)
+                        nxt = 1
+                    else:
+                        b = [t for s in chunk[a_end:] for t in s]
+                        nxt = 0
+                    if a and b:
+                        truncate_seq_pair(a, b, max_tokens)
+                        out.append(TokenInstance(a, b, nxt))
+                chunk, length = [], 0
+            i += 1
+        return out
+
+    # ---- partitions -------------------------------------------------------------------------------------------
+    def save(self, filename: str) -> None:
+        torch.save({"max_seq_length": self.max_seq_length,
+                    "instances": [(x.tokens_a, x.tokens_b, x.is_next) for x in self.instances]}, filename)
+
+    def save_partitions(self, folder: str, n: int) -> List[str]:
+        os.makedirs(folder, exist_ok=True)
+        paths = []
+        for p in range(n):
+            part = self.instances[p::n]
+            path = os.path.join(folder, "part-%05d.pt" % p)
+            torch.save({"max_seq_length": self.max_seq_length, "instances": [(x.tokens_a, x.tokens_b, x.is_next) for x in part]},
+                       path)
+            paths.append(path)
+        return paths
+
+    @staticmethod
+    def load_instances(filename: str) -> List[TokenInstance]:
+        d = torch.load(filename, weights_only=False)
+        return [TokenInstance(list(a), list(b), int(n)) for a, b, n in d["instances"]]
+
+
+GenericPretrainingDataCreator = PretrainingDataCreator
+WikiPretrainingDataCreator = PretrainingDataCreator
+
+
+def get_random_partition(data_directory: str, index: int) -> str:
+    parts = sorted(os.path.join(data_directory, x) for x in os.listdir(data_directory))
+    return parts[index % len(parts)]
+
+
+class BERTDatasetPartitioned(Dataset):
+    """Instances from (up to ``num_partitions``) shards of a folder, masked on the fly (``dataset.py:93-227``:
+    ``masked_lm_prob`` 0.15 capped at ``max_predictions_per_seq``, 80/10/10 replacement).  Returns the same tensor tuple
+    as ``BERTDataset``; ``is_next`` follows OUR loss convention (1 = B really follows A)."""
+
+    def __init__(self, tokenizer: BertTokenizer, folder: str, max_seq_length: int = 128, max_predictions_per_seq: int = 20,
+                 masked_lm_prob: float = 0.15, num_partitions: int = 8, seed: int = 0):
+        self.tokenizer, self.max_seq_length, self.seed = tokenizer, max_seq_length, seed
+        self.max_pred, self.p = max_predictions_per_seq, masked_lm_prob
+        self.vocab_words = list(tokenizer.vocab.keys())
+        seen, self.instances = set(), []
+        for i in range(num_partitions):
+            path = get_random_partition(folder, i)
+            if path not in seen:
+                seen.add(path)
+                self.instances.extend(PretrainingDataCreator.load_instances(path))
+
+    def __len__(self) -> int:
+        return len(self.instances)
+
+    def __getitem__(self, index: int):
+        inst = self.instances[index % len(self.instances)]
+        gen = torch.Generator().manual_seed(self.seed * 1_000_003 + index)
+        a, b = list(inst.tokens_a), list(inst.tokens_b)
+        truncate_seq_pair(a, b, self.max_seq_length - 3)
+        tokens = ["[CLS]"] + a + ["[SEP]"] + b + ["[SEP]"]
+        seg = [0] * (len(a) + 2) + [1] * (len(b) + 1)
+        cand = [i for i, t in enumerate(tokens) if t not in ("[CLS]", "[SEP]")]
+        n_pred = min(self.max_pred, max(1, int(round(len(tokens) * self.p))))
+        order = torch.randperm(len(cand), generator=gen).tolist()[:n_pred]
+        lm = [-1] * len(tokens)
+        unk = self.tokenizer.vocab.get("[UNK]", 0)
+        for j in order:
+            pos = cand[j]
+            lm[pos] = self.tokenizer.vocab.get(tokens[pos], unk)
+            r = float(torch.rand(1, generator=gen))
+            if r < 0.8:
+                tokens[pos] = "[MASK]"
+            elif r < 0.9:
+                tokens[pos] = self.vocab_words[int(torch.randint(len(self.vocab_words), (1,), generator=gen))]
+        ids = self.tokenizer.convert_tokens_to_ids(tokens)
+        pad = self.max_seq_length - len(ids)
+        mask = [1] * len(ids) + [0] * pad
+        ids, seg, lm = ids + [0] * pad, seg + [0] * pad, lm + [-1] * pad
+        return (torch.tensor(ids), torch.tensor(seg), torch.tensor(mask), torch.tensor(lm), torch.tensor(1 - inst.is_next))

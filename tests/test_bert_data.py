@@ -150,3 +150,31 @@ def test_ptb_and_an4_file_loaders(tmp_path):
     assert [AN4_LABELS[int(i)] for i in tgt] == list("HELLO WORLD")
     inputs, targets, pct, sizes = an4_collate([an4[0], an4[1]])
     assert inputs.shape[:3] == (2, 1, 161) and sizes.tolist() == [2, 11] or sizes.tolist() == [11, 2]
+
+
+def test_pretraining_data_creator_partitions_and_partitioned_dataset(tmp_path):
+    """Pre-created instance pipeline (``sources.py`` / ``dataset.py:93-227``): create -> shard -> load -> mask on the fly."""
+    from oktopk_b200.train.bert_data import (BERTDatasetPartitioned, PretrainingDataCreator, TokenInstance,
+                                             get_random_partition, synthetic_corpus)
+    tok = BertTokenizer.synthetic(3000)
+    lines = synthetic_corpus(n_docs=20, sents=6, words=9)
+    (tmp_path / "corpus.txt").write_text("\n".join(lines))
+    pc = PretrainingDataCreator.from_corpus(str(tmp_path / "corpus.txt"), tok, max_seq_length=48, dupe_factor=2, seed=1)
+    assert len(pc) >= 40 and all(isinstance(x, TokenInstance) for x in pc.instances)
+    assert all(len(x.tokens_a) + len(x.tokens_b) <= 45 and x.tokens_a and x.tokens_b for x in pc.instances)
+    frac_random = sum(x.is_next for x in pc.instances) / len(pc)
+    assert 0.2 < frac_random < 0.8
+    paths = pc.save_partitions(str(tmp_path / "parts"), 3)
+    assert len(paths) == 3 and get_random_partition(str(tmp_path / "parts"), 4) == paths[1]
+    ds = BERTDatasetPartitioned(tok, str(tmp_path / "parts"), max_seq_length=48, max_predictions_per_seq=5)
+    assert len(ds) == len(pc)
+    ids, seg, mask, lm, nxt = ds[7]
+    assert ids.shape == seg.shape == mask.shape == lm.shape == (48,) and int(nxt) in (0, 1)
+    n_masked = int((lm != -1).sum())
+    assert 1 <= n_masked <= 5 and int(ids[0]) == tok.vocab["[CLS]"]
+    again = ds[7]
+    assert all(torch.equal(x, y) for x, y in zip(ds[7], again))
+    # <sep>-joined single-line documents (the Wikipedia creator's input format)
+    (tmp_path / "wiki.txt").write_text("\n".join("<sep>".join(lines[i * 7:i * 7 + 6]) for i in range(10)))
+    pw = PretrainingDataCreator.from_corpus(str(tmp_path / "wiki.txt"), tok, sep="<sep>", max_seq_length=32, dupe_factor=1)
+    assert len(pw) > 0
