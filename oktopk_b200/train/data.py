@@ -302,6 +302,7 @@ class Prefetcher:
         self.h2d_bytes = 0
         self._pinned = {}
         self._ring = 0
+        self._ring_events = {}
         self._preload()
 
     def _raw_next(self):
@@ -323,6 +324,9 @@ class Prefetcher:
             return
         # stage through a small ring of reusable pinned buffers (no per-step cudaHostAlloc, no pin thread)
         self._ring = (self._ring + 1) % 3
+        ev = self._ring_events.get(self._ring)
+        if ev is not None:
+            ev.synchronize()          # the host may run steps ahead of the device: never overwrite a slot still being copied
         with torch.cuda.stream(self.stream):
             out = []
             for j, t in enumerate(batch):
@@ -339,6 +343,9 @@ class Prefetcher:
                 else:
                     out.append(t)
             self.next_batch = tuple(out)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+            self._ring_events[self._ring] = done
 
     def next(self, defer: bool = False):
         """The staged batch (device tensors).  With ``defer=True`` the host work for the FOLLOWING batch (collate, pinned
