@@ -185,3 +185,26 @@ def test_vgg16_oktopk_density001_gloo_world2_plumbing():
     k = int(14_728_266 * 0.01)
     assert 0 < modes[0][2] <= 3 * k
     assert out[0][3] == pytest.approx(0.01)
+
+
+def _tiny_worker(rank, P, n):
+    from oktopk_b200.config import OkTopkConfig
+    from oktopk_b200.parallel.algorithms import sparse_allreduce
+    from oktopk_b200.parallel.state import SparseState
+    from oktopk_b200.parallel.world import World
+    w = World()
+    outs = {}
+    for name in ["oktopk", "topkA", "topkA2", "topkAopt", "topkSA", "gaussiank", "gaussiankSA", "gtopk", "none"]:
+        cfg = OkTopkConfig(density=0.001, local_recompute_interval=2, global_recompute_interval=2, repartition_interval=2)
+        st = SparseState(n, P)
+        for it in range(3):
+            g = torch.randn(n, generator=torch.Generator().manual_seed(it * 10 + rank))
+            sparse_allreduce(name, g, st, cfg, w)
+        outs[name] = g.clone()
+    return outs
+
+
+def test_tiny_bucket_gloo_world2_all_schemes():
+    out = run_distributed(_tiny_worker, 2, (10,), backend="gloo", timeout=120)
+    for name, t in out[0].items():
+        assert torch.isfinite(t).all() and torch.equal(t, out[1][name]), name

@@ -197,3 +197,17 @@ def test_state_dict_roundtrip_resumes_identically():
         ob = run_oracle("oktopk", _grads(P, n, it), B, cfg)
         assert torch.equal(oa[0], ob[0])
     assert set(ORACLES) >= {"oktopk", "topkA", "topkA2", "topkAopt", "topkSA", "gtopk", "gaussiank", "gaussiankSA"}
+
+
+@pytest.mark.parametrize("n", [3, 10, 65])
+@pytest.mark.parametrize("P", [1, 2, 4])
+def test_tiny_buckets_are_handled_by_every_scheme(n, P):
+    """Buckets smaller than the world / k = 1 (bias-only buckets happen with small ``bucket_elems``)."""
+    for name in ["oktopk", "topkA", "topkA2", "topkAopt", "topkSA", "gaussiank", "gaussiankSA", "gtopk", "none"]:
+        cfg = OkTopkConfig(density=0.001, local_recompute_interval=2, global_recompute_interval=2, repartition_interval=2)
+        st = [SparseState(n, P) for _ in range(P)]
+        for it in range(4):
+            g = [torch.randn(n, generator=torch.Generator().manual_seed(it * 10 + r)) for r in range(P)]
+            out = run_oracle(name, g, st, cfg)
+            assert all(torch.isfinite(o).all() for o in out), (name, n, P)
+            assert all(torch.equal(o, out[0]) for o in out)
