@@ -65,8 +65,18 @@ class OkTopkConfig:
     backend: str = "auto"               # 'auto' | 'cuda' (fused peer-memory kernels) | 'dist' (torch.distributed ops)
     fused: bool = True                  # one persistent kernel per bucket (False => phase-per-launch ablation)
     deterministic: bool = False         # fixed source order in the sparse reduce (bitwise run-to-run)
-    slot_factor: float = 64.0           # per-(src,dst) slot capacity = slot_factor * k / P (+ pad)
-    gather_factor: float = 64.0         # allgather slot capacity = gather_factor * k / P (+ pad)
+    # Slot capacities.  0 (default) = LOSSLESS: a destination's send slot is as long as its region and the gather slot as
+    # long as the bucket, so no selected entry can ever be dropped, however stale the threshold (the reference gets this
+    # from host-side count handshakes, VGG/allreducer.py:708-726); costs 24 B/element of symmetric memory per bucket.
+    # > 0 = BOUNDED: per-(src,dst) capacity slot_factor * k / P (gather: gather_factor * k / P) with the in-kernel
+    # overflow policy (Ok-Topk: raise the threshold and redo the pack pass; classic-residual schemes keep unsent entries in
+    # the residual) -- 'bounded and conserved'.
+    slot_factor: float = 0.0
+    gather_factor: float = 0.0
+    max_redo: int = 12                  # bounded slots: pack passes that may be repeated per call
+    redo_factor: float = 1.5            # first threshold raise of the overflow policy (squared on every further attempt)
+    land_grads: bool = True             # gradients land in the bucket with ONE multi-tensor copy kernel per bucket (not 1 add/param)
+    nvls: str = "auto"                  # dense path through the NVSwitch multicast object: 'auto' | 'on' | 'off'
     comm_ctas: int = 0                  # CTAs of the persistent kernel (0 => 1 per SM)
     pull_mode: str = "tma"              # 'tma' (cp.async.bulk of remote chunks) | 'ldg' (128-bit peer loads)
     overlap: bool = True                # launch a bucket's exchange as soon as its last grad lands

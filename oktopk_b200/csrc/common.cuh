@@ -68,13 +68,24 @@ __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_re
 // `timeout_ns` the waiter records a fault code in *fault (device memory, read lazily by the host) and gives up,
 // so a dead or wedged peer turns into a reported error instead of a hung GPU.  Once a fault is recorded every
 // later wait of the same bucket returns immediately.
-enum FaultCode : int { FAULT_NONE = 0, FAULT_RS_TIMEOUT = 1, FAULT_AG_TIMEOUT = 2, FAULT_CUT_TIMEOUT = 3, FAULT_DENSE_TIMEOUT = 4 };
+enum FaultCode : int { FAULT_NONE = 0, FAULT_RS_TIMEOUT = 1, FAULT_AG_TIMEOUT = 2, FAULT_CUT_TIMEOUT = 3, FAULT_DENSE_TIMEOUT = 4,
+                       FAULT_TREE_TIMEOUT = 5, FAULT_DONE_TIMEOUT = 6 };
 
 struct SpinGuard {
     int* fault;
     unsigned long long timeout_ns;
     int code;
+    int* host_fault = nullptr;    // mapped pinned mirror of *fault: the host polls it at every step without a sync
 };
+
+// Record a fault once (first writer wins), mirror it to the host.  The fused optimizer kernels read *fault and skip
+// the parameter update, so a partial (timed-out) reduction is never applied.
+__device__ __forceinline__ void raise_fault(const SpinGuard& sg) {
+    if (atomicCAS(sg.fault, FAULT_NONE, sg.code) == FAULT_NONE && sg.host_fault != nullptr) {
+        *reinterpret_cast<volatile int*>(sg.host_fault) = sg.code;
+        __threadfence_system();
+    }
+}
 
 // Spin until the mailbox word carries `epoch` in its high half; returns the low half (payload), 0 on fault.
 __device__ __forceinline__ uint32_t wait_mailbox(const uint64_t* box, uint32_t epoch, const SpinGuard& sg) {
@@ -87,7 +98,7 @@ __device__ __forceinline__ uint32_t wait_mailbox(const uint64_t* box, uint32_t e
         if ((++spins & 1023u) == 0 && sg.fault != nullptr) {
             if (*reinterpret_cast<volatile int*>(sg.fault) != FAULT_NONE) return 0u;
             if (sg.timeout_ns != 0ULL && globaltimer_ns() - t0 > sg.timeout_ns) {
-                atomicCAS(sg.fault, FAULT_NONE, sg.code);
+                raise_fault(sg);
                 return 0u;
             }
         }
@@ -115,6 +126,24 @@ __device__ __forceinline__ void grid_sync(unsigned long long* bar) {
         __threadfence();
     }
     __syncthreads();
+}
+
+// "Last CTA done" ticket: every CTA calls it once when it has finished a phase; exactly one call -- the last one of
+// the grid -- returns true, with all other CTAs' prior global writes visible to it (and, through a subsequent
+// system-scope release, to peers).  Replaces a grid barrier wherever only ONE thread has to act on "everybody is done"
+// (publishing a count to the peers): nobody waits, the counter resets itself.
+__device__ __forceinline__ bool last_cta_ticket(unsigned int* ticket) {
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int old = atomicAdd(ticket, 1u);
+        const int last = (old == gridDim.x - 1u) ? 1 : 0;
+        if (last) { __threadfence(); *reinterpret_cast<volatile unsigned int*>(ticket) = 0u; }
+        s_last = last;
+    }
+    __syncthreads();
+    return s_last != 0;
 }
 
 // ----------------------------------------------------------------------------------------

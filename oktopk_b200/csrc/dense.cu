@@ -5,6 +5,15 @@
 // shard): a start barrier (everyone's backward has produced the bucket) and an end barrier
 // (everyone's stores have landed) built from st.release.sys / ld.acquire.sys flags.
 //
+// Two data paths behind the same barriers:
+//   * NVLS (p.mc != null): the bucket is also mapped through an NVSwitch MULTICAST object; `multimem.ld_reduce`
+//     lets the switch add the P copies of a vector on the fly (one load returns the sum) and `multimem.st`
+//     broadcasts the averaged vector to all P buckets with one store -- each GPU moves n/P in and n/P out over its
+//     links instead of (P-1)/P*n each way;
+//   * peer loads/stores (no multicast mapping): the owner reads the P copies with 128-bit peer loads.
+// The launch is cooperative: the per-CTA cross-GPU barriers need CTA i of every rank to be resident, which a plain
+// launch does not guarantee while backward kernels still hold SMs.
+//
 // Serves the dense baseline (`compressor none`), the dense warm-up iterations of every sparse
 // scheme and TopkDSA's dense fallback -- reference: dense_allreduce / _dense_allreduce,
 // VGG/allreducer.py:175-180,532-547 (host MPI.Allreduce on NumPy buffers).
@@ -32,7 +41,10 @@ __device__ __forceinline__ void cta_peer_barrier(const DenseParams& p, int phase
             __nanosleep(20);
             if ((++spins & 1023u) == 0 && p.fault != nullptr) {
                 if (*reinterpret_cast<volatile int*>(p.fault) != FAULT_NONE) break;
-                if (p.timeout_ns != 0ULL && globaltimer_ns() - t0 > p.timeout_ns) { atomicCAS(p.fault, FAULT_NONE, FAULT_DENSE_TIMEOUT); break; }
+                if (p.timeout_ns != 0ULL && globaltimer_ns() - t0 > p.timeout_ns) {
+                    raise_fault(SpinGuard{p.fault, p.timeout_ns, FAULT_DENSE_TIMEOUT, p.host_fault});
+                    break;
+                }
             }
         }
     }
@@ -54,6 +66,30 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_allreduce_kernel(const
     const int lo = rank * shard4;
     const int hi = min(n4, lo + shard4);
     const float scale = p.scale;
+    if (p.mc != nullptr) {
+        // ---- NVLS: reduce in the switch, broadcast through the switch ---------------------------------------------
+        float4* mc4 = reinterpret_cast<float4*>(p.mc);
+        constexpr int kU = 4;                            // independent multimem loads in flight per thread
+        const int trip = gridDim.x * kDenseThreads * kU;
+        for (int base = lo + blockIdx.x * kDenseThreads * kU; base < hi; base += trip) {
+            float4 acc[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int v = base + u * kDenseThreads + threadIdx.x;
+                if (v < hi)
+                    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                 : "=f"(acc[u].x), "=f"(acc[u].y), "=f"(acc[u].z), "=f"(acc[u].w) : "l"(mc4 + v) : "memory");
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int v = base + u * kDenseThreads + threadIdx.x;
+                if (v < hi)
+                    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+                                 ::"l"(mc4 + v), "f"(acc[u].x * scale), "f"(acc[u].y * scale), "f"(acc[u].z * scale),
+                                   "f"(acc[u].w * scale) : "memory");
+            }
+        }
+    } else {
     // kDenseTile vectors per thread per trip and all P peer loads of a vector issued back to back: NVLink
     // round trips are ~2-3 us, so bandwidth is bought with bytes in flight (512 thr x 2 x P x 16 B per SM).
     const int trip = gridDim.x * kDenseThreads * kDenseTile;
@@ -97,6 +133,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_allreduce_kernel(const
             }
         }
     }
+    }
     // scalar tail (n % 4) is reduced by rank 0's CTA 0
     if (rank == 0 && blockIdx.x == 0) {
         for (int i = n4 * 4 + threadIdx.x; i < p.n; i += kDenseThreads) {
@@ -112,8 +149,8 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_allreduce_kernel(const
 }
 
 cudaError_t launch_dense_allreduce(const DenseParams& p, int grid, cudaStream_t stream) {
-    dense_allreduce_kernel<<<grid, kDenseThreads, 0, stream>>>(p);
-    return cudaGetLastError();
+    void* args[] = {(void*)&p};
+    return cudaLaunchCooperativeKernel((void*)dense_allreduce_kernel, dim3(grid), dim3(kDenseThreads), args, 0, stream);
 }
 
 }  // namespace okt

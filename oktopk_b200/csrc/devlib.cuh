@@ -24,11 +24,19 @@ __device__ __forceinline__ uint64_t* cut_mbox(char* b, const SymmLayout& L, int 
 __device__ __forceinline__ int* cut_data(char* b, const SymmLayout& L, int par, int src) {
     return reinterpret_cast<int*>(b + L.cut_data) + (par * OKT_MAXP + src) * OKT_MAXP;
 }
-__device__ __forceinline__ int* send_idx(char* b, const SymmLayout& L, int P, int par, int dst) {
-    return reinterpret_cast<int*>(b + L.send_idx) + ((size_t)par * P + dst) * L.cap;
+__device__ __forceinline__ uint64_t* done_mbox(char* b, const SymmLayout& L, int par, int src) {
+    return reinterpret_cast<uint64_t*>(b + L.done_mbox) + par * OKT_MAXP + src;
 }
-__device__ __forceinline__ float* send_val(char* b, const SymmLayout& L, int P, int par, int dst) {
-    return reinterpret_cast<float*>(b + L.send_val) + ((size_t)par * P + dst) * L.cap;
+__device__ __forceinline__ uint64_t* tree_mbox(char* b, const SymmLayout& L, int par, int src) {
+    return reinterpret_cast<uint64_t*>(b + L.tree_mbox) + par * OKT_MAXP + src;
+}
+// send slots: base of the (single-buffered) send buffer; destination d's slot starts at slot_off(d) entries
+__device__ __forceinline__ int* send_idx_base(char* b, const SymmLayout& L) { return reinterpret_cast<int*>(b + L.send_idx); }
+__device__ __forceinline__ float* send_val_base(char* b, const SymmLayout& L) { return reinterpret_cast<float*>(b + L.send_val); }
+// lossless layout: the slot of region d starts at align4(edges[d]) + 4 d (16-byte aligned for TMA, capacity >= the
+// region's length); bounded layout: d * cap
+__device__ __forceinline__ int slot_off(const SymmLayout& L, const int* edges, int d) {
+    return L.cap > 0 ? d * L.cap : ((edges[d] + 3) & ~3) + 4 * d;
 }
 __device__ __forceinline__ int* gat_idx(char* b, const SymmLayout& L, int par) {
     return reinterpret_cast<int*>(b + L.gat_idx) + (size_t)par * L.gcap;

@@ -7,6 +7,11 @@
 // Behaviour: SURVEY Appendix B.1 / B.3 / B.6 (reference VGG/allreducer.py:34-69,1100-1150,
 // 1420-1465; VGG/compression.py:37-62,220-266).  The reference's <=20 rescans of Gaussiank are
 // replaced by ONE ladder-histogram pass that yields the count at every candidate threshold.
+//
+// TopkA2 (reselect, VGG/allreducer.py:519-525 + VGG/compression.py:151-160): after the P slots have been added, the
+// union of the gathered indices (exact first-touch detection through a bitmap) is re-selected down to the global
+// top-k with the grid-wide radix select, the losers are zeroed, and every rank puts its own non-surviving picks back
+// into its residual.  norm_clip (VGG/allreducer.py:1372-1379): one extra L2-norm pass scales the incoming gradient.
 #include "devlib.cuh"
 
 namespace okt {
@@ -42,6 +47,23 @@ __global__ void __launch_bounds__(kThreads, 2) gather_scheme_kernel(const Gather
     const int n4 = n >> 2;
     float4* g4 = reinterpret_cast<float4*>(p.g);
     float4* r4 = reinterpret_cast<float4*>(p.res);
+
+    // ---------------------------------------------------------------- norm_clip: ||g||_2 <= clip_max_norm
+    float gscale = 1.f;
+    if (p.clip_max_norm > 0.f) {
+        double ss = 0.0;
+        for (int v = gtid; v < n4; v += gthreads) {
+            const float4 a = ld_stream_f4(g4 + v);
+            ss += (double)a.x * a.x + (double)a.y * a.y + (double)a.z * a.z + (double)a.w * a.w;
+        }
+        if (blockIdx.x == 0)
+            for (int i = n4 * 4 + tid; i < n; i += kThreads) ss += (double)p.g[i] * p.g[i];
+        ss = warp_sum_d(ss);
+        if (lane == 0 && ss != 0.0) atomicAdd(&st->clip_sumsq, ss);
+        grid_sync(&st->bar);
+        const double nrm = sqrt(*reinterpret_cast<volatile double*>(&st->clip_sumsq));
+        if (nrm > (double)p.clip_max_norm && nrm > 0.0) gscale = (float)((double)p.clip_max_norm / nrm);
+    }
     const bool single_pass = (p.select_mode == GS_THRESHOLD_REUSE) && !p.exact_now;
     const bool need_kth = (p.select_mode == GS_EXACT_TOPK) || (p.select_mode == GS_THRESHOLD_REUSE && p.exact_now);
     const bool inclusive = p.select_mode == GS_EXACT_TOPK;     // exact top-k keeps the k-th element itself
@@ -56,21 +78,21 @@ __global__ void __launch_bounds__(kThreads, 2) gather_scheme_kernel(const Gather
         for (int v = gtid; v < n4; v += gthreads) {
             float4 a = ld_stream_f4(g4 + v);
             float4 r = ld_stream_f4(r4 + v);
-            a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+            a.x = a.x * gscale + r.x; a.y = a.y * gscale + r.y; a.z = a.z * gscale + r.z; a.w = a.w * gscale + r.w;
             st_stream_f4(r4 + v, a);
             st_stream_f4(g4 + v, make_float4(0.f, 0.f, 0.f, 0.f));
             visit(a.x); visit(a.y); visit(a.z); visit(a.w);
         }
         if (blockIdx.x == 0)
             for (int i = n4 * 4 + tid; i < n; i += kThreads) {
-                float a = p.g[i] + p.res[i];
+                float a = p.g[i] * gscale + p.res[i];
                 p.res[i] = a;
                 p.g[i] = 0.f;
                 visit(a);
             }
         if (need_kth) {
             hist_flush(st, s_hist);
-            Seg seg{p.res, n};
+            Seg seg{p.res, n, nullptr};
             float thr = grid_kth_abs(&seg, 1, false, (uint32_t)p.k, st, s_hist, s_w, 1);
             if (blockIdx.x == 0 && tid == 0) { st->local_thr = thr; st->local_thr_used = thr; }
             grid_sync(&st->bar);
@@ -165,7 +187,7 @@ __global__ void __launch_bounds__(kThreads, 2) gather_scheme_kernel(const Gather
                 if (single_pass) {
                     a = ld_stream_f4(g4 + v);
                     float4 r = ld_stream_f4(r4 + v);
-                    a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+                    a.x = a.x * gscale + r.x; a.y = a.y * gscale + r.y; a.z = a.z * gscale + r.z; a.w = a.w * gscale + r.w;
                     st_stream_f4(r4 + v, a);
                     st_stream_f4(g4 + v, make_float4(0.f, 0.f, 0.f, 0.f));
                 } else {
@@ -184,14 +206,14 @@ __global__ void __launch_bounds__(kThreads, 2) gather_scheme_kernel(const Gather
             bool in = i < n;
             float a = 0.f;
             if (in) {
-                if (single_pass) { a = p.g[i] + p.res[i]; p.res[i] = a; p.g[i] = 0.f; }
+                if (single_pass) { a = p.g[i] * gscale + p.res[i]; p.res[i] = a; p.g[i] = 0.f; }
                 else a = p.res[i];
             }
             emit(i, a, in);
         }
         int ssum = warp_sum(selected), dsum = warp_sum(dropped);
         if (lane == 0 && ssum) atomicAdd(&st->guard_counts[0], ssum);
-        if (lane == 0 && dsum) atomicAdd(&st->stat_overflow_gather, dsum);
+        if (lane == 0 && dsum) atomicAdd(&st->cum_overflow_gather, (unsigned long long)dsum);
         grid_sync(&st->bar);
     }
 
@@ -208,7 +230,7 @@ __global__ void __launch_bounds__(kThreads, 2) gather_scheme_kernel(const Gather
         __syncthreads();
         if (tid == 0) st->gather_cursor = 0;
     }
-    if (tid < P) s_cnt[tid] = (int)wait_mailbox(ag_mbox(me, p.L, par, tid), epoch, SpinGuard{&st->fault, p.timeout_ns, FAULT_AG_TIMEOUT});
+    if (tid < P) s_cnt[tid] = (int)wait_mailbox(ag_mbox(me, p.L, par, tid), epoch, SpinGuard{&st->fault, p.timeout_ns, FAULT_AG_TIMEOUT, p.host_fault});
     __syncthreads();
     {
         // Every rank reduces all P slots itself (no owner), so the order of the floating-point additions must be the
@@ -220,17 +242,77 @@ __global__ void __launch_bounds__(kThreads, 2) gather_scheme_kernel(const Gather
         for (int s = 0; s < P; ++s) {
             ChunkSrc src{gat_idx(p.peers[s], p.L, par), gat_val(p.peers[s], p.L, par), s_cnt[s]};
             T += s_cnt[s];
-            pull_chunks(&src, 1, p.pull_tma != 0, &s_pull, pipe_it, [&](int, int idx, float val) {
-                if ((unsigned)idx < (unsigned)n) red_add_f32(p.g + idx, val / fP);
-            });
+            if (!p.reselect) {
+                pull_chunks(&src, 1, p.pull_tma != 0, &s_pull, pipe_it, [&](int, int idx, float val) {
+                    if ((unsigned)idx < (unsigned)n) red_add_f32(p.g + idx, val / fP);
+                });
+            } else {
+                // TopkA2: also build the list of DISTINCT gathered indices (bitmap = exact first-touch detection)
+                pull_chunks(&src, 1, p.pull_tma != 0, &s_pull, pipe_it, [&](int, int idx, float val) {
+                    const bool ok = (unsigned)idx < (unsigned)n;
+                    bool first = false;
+                    if (ok) {
+                        red_add_f32(p.g + idx, val / fP);
+                        const unsigned bit = 1u << (idx & 31);
+                        first = (atomicOr(p.bitmap + (idx >> 5), bit) & bit) == 0u;
+                    }
+                    const int pos = warp_append_active(&st->cand_cursor, first);
+                    if (first && pos < p.ccap) p.cand[pos] = idx;
+                });
+            }
             grid_sync(&st->bar);
+        }
+        int kept_total = T;
+        if (p.reselect) {
+            const int ncand = min(*reinterpret_cast<volatile int*>(&st->cand_cursor), p.ccap);
+            float thr2 = 0.f;
+            if (ncand > p.k) {                               // more than k distinct indices: keep the global top-k
+                Seg seg{p.g, ncand, p.cand};
+                thr2 = grid_kth_abs(&seg, 1, false, (uint32_t)p.k, st, s_hist, s_w, 0);
+            }
+            // put my own non-surviving picks back into my residual (it was zeroed at the selection)
+            {
+                const int* mi = gat_idx(me, p.L, par);
+                const float* mv = gat_val(me, p.L, par);
+                const int mine = s_cnt[rank];
+                for (int e = gtid; e < mine; e += gthreads) {
+                    const int idx = mi[e];
+                    if ((unsigned)idx < (unsigned)n && fabsf(__ldcg(p.g + idx)) < thr2) p.res[idx] += mv[e];
+                }
+            }
+            grid_sync(&st->bar);
+            int kept = 0;
+            for (int c = gtid; c < ncand; c += gthreads) {
+                const int idx = __ldcg(p.cand + c);
+                if (fabsf(__ldcg(p.g + idx)) < thr2) p.g[idx] = 0.f; else kept++;
+                p.bitmap[idx >> 5] = 0u;                     // leave the bitmap all-zero for the next call
+            }
+            kept = warp_sum(kept);
+            if (lane == 0 && kept) atomicAdd(&st->stat_global_count, kept);
+            grid_sync(&st->bar);
+            kept_total = *reinterpret_cast<volatile int*>(&st->stat_global_count);
         }
         if (blockIdx.x == 0 && tid == 0) {
             st->epoch = epoch;
             st->stat_gather_total = T;
-            st->stat_global_count = T;
+            st->stat_global_count = kept_total;
+            st->cand_cursor = 0;
+            st->clip_sumsq = 0.0;
+            const unsigned long long og = *reinterpret_cast<volatile unsigned long long*>(&st->cum_overflow_gather);
+            st->stat_overflow_gather = (int)min(og - st->snap_overflow_gather, 0x7fffffffULL);
+            st->snap_overflow_gather = og;
+            st->stat_overflow_send = 0;
         }
     }
+}
+
+int gather_max_coop_grid(int device) {
+    int sms = 0, per = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, gather_scheme_kernel, kThreads, 0);
+    if (per < 1) per = 1;
+    if (per > 2) per = 2;
+    return sms * per;
 }
 
 cudaError_t launch_gather_scheme(const GatherParams& p, int grid, cudaStream_t stream) {

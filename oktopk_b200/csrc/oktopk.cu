@@ -12,9 +12,14 @@
 // (reference: VGG/allreducer.py:575-1098, BERT/bert/allreducer.py:357-743,
 // VGG/compression.py:370-415,467-471) -- the data flow here is a redesign, not a translation:
 // the reference sizes every receive buffer from host Alltoall/Allgather handshakes and stages
-// all payloads through NumPy; here slots are fixed-capacity peer-visible buffers, counts travel
-// as release/acquire flags, and the over-selection guard is applied receiver-side so that the
-// common iteration is a single streaming pass (16 B/element).
+// all payloads through NumPy; here slots are peer-visible buffers whose capacity covers the whole
+// destination region (lossless layout, oktopk.cuh) or, in the bounded layout, are protected by an
+// in-kernel overflow policy (raise the threshold, redo the pack pass: nothing selected is ever
+// lost), counts travel as release/acquire flags, and the over-selection guard is applied
+// receiver-side so that the common iteration is a single streaming pass (16 B/element).
+// Grid-wide synchronisation: ONE grid barrier per call (reduce -> global selection); "everybody
+// finished packing / selecting" is a last-CTA ticket whose winner publishes the counts, and the
+// rank's own mailbox doubles as the local barrier of the next phase.
 #include "devlib.cuh"
 
 namespace okt {
@@ -36,6 +41,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
     __shared__ int s_cnt[OKT_MAXP];
     __shared__ float s_thr[OKT_MAXP];
     __shared__ int s_misc[OKT_MAXP * 2 + 4];
+    __shared__ int s_soff[OKT_MAXP + 1];            // send-slot offsets (entries) per destination, see slot_off()
+    __shared__ ChunkSrc s_srcs[OKT_MAXP];
+    __shared__ float s_sthr[OKT_MAXP];
+    __shared__ Seg s_segs[OKT_MAXP];
     __shared__ __align__(128) PullSmem s_pull;
     __shared__ __align__(8) uint64_t s_pk_bar[kPackStages];
     __shared__ __align__(8) uint64_t s_pk_empty[kPackStages];
@@ -54,6 +63,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
     uint32_t pipe_it = 0;
 
     for (int b = tid; b < kHistBins; b += kThreads) s_hist[b] = 0;
+    if (blockIdx.x == 0 && tid == 0) st->t_phase[5] = globaltimer_ns();
+    const SpinGuard sg_rs{&st->fault, p.timeout_ns, FAULT_RS_TIMEOUT, p.host_fault};
+    const SpinGuard sg_ag{&st->fault, p.timeout_ns, FAULT_AG_TIMEOUT, p.host_fault};
+    const SpinGuard sg_cut{&st->fault, p.timeout_ns, FAULT_CUT_TIMEOUT, p.host_fault};
+    const SpinGuard sg_done{&st->fault, p.timeout_ns, FAULT_DONE_TIMEOUT, p.host_fault};
     if (tid == 0) {
         mbar_init(&s_pull.bar[0], 1);
         mbar_init(&s_pull.bar[1], 1);
@@ -173,7 +187,6 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
                 thr = grid_kth_abs(&seg, 1, false, (uint32_t)p.k, st, s_hist, s_w, /*first_pass=*/prefilter ? 0 : 1);
             }
             if (blockIdx.x == 0 && tid == 0) { st->local_thr_used = thr; st->cand_cursor = 0; }
-            if (blockIdx.x == 0 && tid == 0) st->local_thr_used = thr;
         } else {
 #pragma unroll
             for (int j = 0; j < kGuardMax; ++j) {
@@ -264,7 +277,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
                     for (int j = 0; j < P - 1; ++j) st_relaxed_sys_u32(reinterpret_cast<uint32_t*>(dst + j), (uint32_t)st->cuts[j]);
                     st_release_sys_u64(cut_mbox(p.peers[tid], p.L, par, rank), make_mail(epoch, 1u));
                 }
-                if (tid < P) wait_mailbox(cut_mbox(me, p.L, par, tid), epoch, SpinGuard{&st->fault, p.timeout_ns, FAULT_CUT_TIMEOUT});
+                if (tid < P) wait_mailbox(cut_mbox(me, p.L, par, tid), epoch, sg_cut);
                 __syncthreads();
                 if (tid < P - 1) {
                     long long sum = 0;
@@ -289,272 +302,324 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
         }
     }
 
-    // region edges for this call
+    // region edges and send-slot offsets for this call
     if (tid <= P) s_edges[tid] = st->edges[tid];
     __syncthreads();
+    if (tid <= P) s_soff[tid] = (tid < P) ? slot_off(p.L, s_edges, tid) : (p.L.cap > 0 ? P * p.L.cap : slot_off(p.L, s_edges, P));
+    __syncthreads();
+    int* const my_sidx = send_idx_base(me, p.L);
+    float* const my_sval = send_val_base(me, p.L);
     // per-phase device timestamps (observability: the reference's _compression/_allreduce wall-clock timers)
     auto stamp = [&](int slot) { if (blockIdx.x == 0 && tid == 0) st->t_phase[slot] = globaltimer_ns(); };
     stamp(0);
 
-    // ======================================================================== PH_PACK
+    // ======================================================================== PH_PACK (+ publish to the region owners)
     if (p.phase_begin <= PH_PACK && PH_PACK < p.phase_end) {
-        const float thr_sel = two_pass ? st->local_thr_used : st->local_thr;
-        float lad[kGuardMax];
-        lad[0] = thr_sel;
-#pragma unroll
-        for (int j = 1; j < kGuardMax; ++j) lad[j] = lad[j - 1] * p.guard_factor;
-        int gc[kGuardMax];
-#pragma unroll
-        for (int j = 0; j < kGuardMax; ++j) gc[j] = 0;
+        float thr_sel = two_pass ? st->local_thr_used : st->local_thr;
+        const bool bounded = p.L.cap > 0;
+        // Overflow policy of the bounded layout (Ok-Topk residual rule): if a destination's slot is full, raise the threshold
+        // and redo the pack pass from the accumulator (already in the residual buffer).  Everything above the final
+        // threshold is then in the slots, everything below stays in the residual: nothing selected is lost.  The decision
+        // is taken identically by every CTA from the slot cursors after a grid barrier.  Classic-residual schemes
+        // (TopkDSA / gaussiankSA) zero the residual only for entries that found room, so an unsent entry stays put.
+        const bool can_redo = bounded && p.residual_mode == RES_OKTOPK && p.max_redo > 0;
+        float redo_f = p.redo_factor > 1.f ? p.redo_factor : 1.5f;
+        int attempt = 0;
         int dropped = 0;
-        const int cap = p.L.cap;
-        if (blockIdx.x == 0 && tid == 0) { st->stat_global_count = 0; st->stat_recv_total = 0; }
+        if (blockIdx.x == 0 && tid == 0) { st->stat_global_count = 0; st->stat_recv_total = 0; st->stat_dense_fallback = 0; }
 
-        // one element per lane; every lane of the warp calls this (converged)
-        auto emit = [&](int i, float x, bool inrange) {
-            const float ax = fabsf(x);
-            const bool pred = inrange && ax > thr_sel;
-            unsigned todo = __ballot_sync(0xffffffffu, pred);
-            if (todo == 0) return;
-            int d = 0;
-            if (pred) {
-                d = region_of(s_edges, P, i);
-                gc[0]++;
-                if (!two_pass) {
-#pragma unroll
-                    for (int j = 1; j < kGuardMax; ++j) gc[j] += (j <= p.guard_loops && ax > lad[j]) ? 1 : 0;
-                }
-            }
-            while (todo) {
-                const int leader = __ffs(todo) - 1;
-                const int dl = __shfl_sync(0xffffffffu, d, leader);
-                const bool mine = pred && d == dl;
-                const unsigned m = __ballot_sync(0xffffffffu, mine);
-                int base = 0;
-                if (lane == leader) base = atomicAdd(&st->send_cursor[dl], __popc(m));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (mine) {
-                    int pos = base + __popc(m & ((1u << lane) - 1u));
-                    if (pos < cap) {
-                        send_idx(me, p.L, P, par, dl)[pos] = i - s_edges[dl];
-                        send_val(me, p.L, P, par, dl)[pos] = x;
-                    } else {
-                        dropped++;
-                    }
-                }
-                todo &= ~m;
-            }
-            if (p.residual_mode != RES_OKTOPK && pred) p.res[i] = 0.f;   // classic local error feedback
-        };
-
-        // Streaming pass fed by TMA: the CTA walks its tiles (kPackTile x 512 float4 = 16 KB of the gradient + 16 KB of
-        // the residual each) through a kPackStages-deep shared-memory ring.  One elected thread arms the stage's mbarrier
-        // (expect_tx) and issues the two cp.async.bulk loads kPackStages-1 tiles ahead, so ~96 KB of reads per SM are in
-        // flight independent of occupancy/register budget; consumers read the tile with conflict-free LDS.128, write the
-        // accumulator / the zeroed bucket back with streaming 128-bit stores (posted), and run the selection.
-        // 16 B/element of HBM traffic: the roofline floor of the whole call.
         float4* pk_r = dyn_pk;                                          // [kPackStages][kTileV]
         float4* pk_g = dyn_pk + kPackStages * kTileV;                   // [kPackStages][kTileV]
         const int ntiles = (n4 + kTileV - 1) / kTileV;
         const int G = gridDim.x;
         const int nmine = (ntiles > (int)blockIdx.x) ? (ntiles - (int)blockIdx.x + G - 1) / G : 0;
-        auto arm = [&](int j) {                                         // thread 0 only
-            const int tile = blockIdx.x + j * G;
-            const int stg = j % kPackStages;
-            const uint32_t bytes = (uint32_t)min(kTileV, n4 - tile * kTileV) * 16u;
-            fence_proxy_async_all();
-            mbar_expect_tx(&s_pk_bar[stg], two_pass ? bytes : 2u * bytes);
-            tma_load_1d(pk_r + stg * kTileV, r4 + (size_t)tile * kTileV, bytes, &s_pk_bar[stg]);
-            if (!two_pass) tma_load_1d(pk_g + stg * kTileV, g4 + (size_t)tile * kTileV, bytes, &s_pk_bar[stg]);
-        };
-        if (tid == 0)
-            for (int j = 0; j < min(nmine, kPackStages - 1); ++j) arm(j);
-        for (int j = 0; j < nmine; ++j) {
-            // Producer (thread 0): re-arm the stage tile j-1 used, once all kWarps warps have released it (per-stage
-            // "empty" mbarrier; no block-wide barrier per tile, so a warp waiting for its slot reservation does not
-            // hold up the other 15 -- they may run up to kPackStages-1 tiles ahead).
-            if (tid == 0 && j + kPackStages - 1 < nmine) {
-                if (j >= 1) mbar_wait(&s_pk_empty[(j - 1) % kPackStages], (uint32_t)((j - 1) / kPackStages) & 1u);
-                arm(j + kPackStages - 1);
-            }
-            const int stg = j % kPackStages;
-            mbar_wait(&s_pk_bar[stg], (uint32_t)(j / kPackStages) & 1u);
-            const int base = (blockIdx.x + j * G) * kTileV;
-            float4 a[kPackTile];
-            bool in[kPackTile];
+        int ring_it = 0;                                                // tiles this CTA has pushed through the ring so far
+
+        while (true) {
+            const bool res_only = two_pass || attempt > 0;              // the accumulator is already in the residual buffer
+            const bool ladder_on = !two_pass;                           // count the guard ladder in this pass
+            float lad[kGuardMax];
+            lad[0] = thr_sel;
 #pragma unroll
-            for (int u = 0; u < kPackTile; ++u) {
-                const int v = base + u * kThreads + tid;
-                in[u] = v < n4;
-                a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (in[u]) {
-                    a[u] = pk_r[stg * kTileV + u * kThreads + tid];
-                    if (!two_pass) {
-                        const float4 gq = pk_g[stg * kTileV + u * kThreads + tid];
-                        a[u].x += gq.x; a[u].y += gq.y; a[u].z += gq.z; a[u].w += gq.w;
-                        st_stream_f4(r4 + v, a[u]);
-                    }
-                    st_stream_f4(g4 + v, make_float4(0.f, 0.f, 0.f, 0.f));
-                }
-            }
-            __syncwarp();                                               // the warp's part of the tile is in registers:
-            if (lane == 0) mbar_arrive(&s_pk_empty[stg]);               // release the stage (1 of kWarps arrivals)
-            // ---- selection: one slot reservation per (warp, trip, destination) ------------------------------
-            // 16 element flags per lane -> 16 ballots; the warp's trip covers 4 windows of 128 consecutive elements,
-            // which (regions being contiguous ranges) almost always belong to ONE destination, so the append costs
-            // one global atomic per trip instead of one per selected vector component.
-            unsigned msk[kPackTile * 4];
-            unsigned mybits = 0u;
-            int tot = 0;
+            for (int j = 1; j < kGuardMax; ++j) lad[j] = lad[j - 1] * p.guard_factor;
+            int gc[kGuardMax];
 #pragma unroll
-            for (int u = 0; u < kPackTile; ++u) {
-                const float xs[4] = {a[u].x, a[u].y, a[u].z, a[u].w};
+            for (int j = 0; j < kGuardMax; ++j) gc[j] = 0;
+            dropped = 0;
+
+            // one element per lane; every lane of the warp calls this (converged) -- scalar tail only
+            auto emit = [&](int i, float x, bool inrange) {
+                const float ax = fabsf(x);
+                const bool pred = inrange && ax > thr_sel;
+                unsigned todo = __ballot_sync(0xffffffffu, pred);
+                if (todo == 0) return;
+                int d = 0;
+                if (pred) {
+                    d = region_of(s_edges, P, i);
+                    gc[0]++;
+                    if (ladder_on) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const bool pred = in[u] && fabsf(xs[c]) > thr_sel;
-                    // TopkDSA zeroes the residual at the exact top-k INCLUDING the k-th element itself, which the
-                    // strict '>' select does not send (reference quirk): a rare, direct store
-                    if (p.residual_mode == RES_LOCAL_GE && in[u] && xs[c] != 0.f && fabsf(xs[c]) == thr_sel)
-                        p.res[4 * (base + u * kThreads + tid) + c] = 0.f;
-                    const unsigned m = __ballot_sync(0xffffffffu, pred);
-                    msk[u * 4 + c] = m;
-                    tot += __popc(m);
-                    if (pred) mybits |= 1u << (u * 4 + c);
-                }
-            }
-            if (tot == 0) continue;
-            // guard ladder / residual side effects of my selected elements
-#pragma unroll
-            for (int u = 0; u < kPackTile; ++u) {
-                const float xs[4] = {a[u].x, a[u].y, a[u].z, a[u].w};
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    if (mybits & (1u << (u * 4 + c))) {
-                        const float ax = fabsf(xs[c]);
-                        gc[0]++;
-                        if (!two_pass) {
-#pragma unroll
-                            for (int j = 1; j < kGuardMax; ++j) gc[j] += (j <= p.guard_loops && ax > lad[j]) ? 1 : 0;
-                        }
-                        if (p.residual_mode != RES_OKTOPK) p.res[4 * (base + u * kThreads + tid) + c] = 0.f;
+                        for (int j = 1; j < kGuardMax; ++j) gc[j] += (j <= p.guard_loops && ax > lad[j]) ? 1 : 0;
                     }
                 }
-            }
-            const int e_first = 4 * (base + (warp << 5));
-            const int e_last = min(n - 1, 4 * (base + (kPackTile - 1) * kThreads + (warp << 5) + 31) + 3);
-            const int dlo = region_of(s_edges, P, e_first), dhi = region_of(s_edges, P, e_last);
-            for (int d = dlo; d <= dhi; ++d) {
-                unsigned md[kPackTile * 4];
-                unsigned mine = mybits;
-                int cnt = 0;
-                if (dlo == dhi) {
-#pragma unroll
-                    for (int q = 0; q < kPackTile * 4; ++q) { md[q] = msk[q]; cnt += __popc(md[q]); }
-                } else {
-                    const int lo_d = s_edges[d], hi_d = s_edges[d + 1];
-                    mine = 0u;
-#pragma unroll
-                    for (int u = 0; u < kPackTile; ++u) {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const int i = 4 * (base + u * kThreads + tid) + c;
-                            const bool pd = ((mybits >> (u * 4 + c)) & 1u) && i >= lo_d && i < hi_d;
-                            md[u * 4 + c] = __ballot_sync(0xffffffffu, pd);
-                            cnt += __popc(md[u * 4 + c]);
-                            if (pd) mine |= 1u << (u * 4 + c);
+                while (todo) {
+                    const int leader = __ffs(todo) - 1;
+                    const int dl = __shfl_sync(0xffffffffu, d, leader);
+                    const bool mine = pred && d == dl;
+                    const unsigned m = __ballot_sync(0xffffffffu, mine);
+                    int base = 0;
+                    if (lane == leader) base = atomicAdd(&st->send_cursor[dl], __popc(m));
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    if (mine) {
+                        const int pos = base + __popc(m & ((1u << lane) - 1u));
+                        if (pos < s_soff[dl + 1] - s_soff[dl]) {
+                            my_sidx[s_soff[dl] + pos] = i - s_edges[dl];
+                            my_sval[s_soff[dl] + pos] = x;
+                            if (p.residual_mode != RES_OKTOPK) p.res[i] = 0.f;   // classic local error feedback: sent => cleared
+                        } else {
+                            dropped++;                                           // no room: the entry stays in the residual
                         }
                     }
+                    todo &= ~m;
                 }
-                if (cnt == 0) continue;
-                int run = 0;
-                if (lane == 0) run = atomicAdd(&st->send_cursor[d], cnt);
-                run = __shfl_sync(0xffffffffu, run, 0);
-                int* sidx = send_idx(me, p.L, P, par, d);
-                float* sval = send_val(me, p.L, P, par, d);
-                const int off_d = s_edges[d];
-                const unsigned lt = (1u << lane) - 1u;
+            };
+
+            // Streaming pass fed by TMA: the CTA walks its tiles (kPackTile x 512 float4 = 16 KB of the gradient + 16 KB of
+            // the residual each) through a kPackStages-deep shared-memory ring.  One elected thread arms the stage's mbarrier
+            // (expect_tx) and issues the two cp.async.bulk loads kPackStages-1 tiles ahead, so ~96 KB of reads per SM are in
+            // flight independent of occupancy/register budget; consumers read the tile with conflict-free LDS.128, write the
+            // accumulator / the zeroed bucket back with streaming 128-bit stores (posted), and run the selection.
+            // 16 B/element of HBM traffic: the roofline floor of the whole call.
+            // (The ring's mbarrier phases run on across redo passes: ring_it counts every tile ever pushed through.)
+            auto arm = [&](int j) {                                         // thread 0 only; j = tile number of THIS pass
+                const int tile = blockIdx.x + j * G;
+                const int stg = (ring_it + j) % kPackStages;
+                const uint32_t bytes = (uint32_t)min(kTileV, n4 - tile * kTileV) * 16u;
+                fence_proxy_async_all();
+                mbar_expect_tx(&s_pk_bar[stg], res_only ? bytes : 2u * bytes);
+                tma_load_1d(pk_r + stg * kTileV, r4 + (size_t)tile * kTileV, bytes, &s_pk_bar[stg]);
+                if (!res_only) tma_load_1d(pk_g + stg * kTileV, g4 + (size_t)tile * kTileV, bytes, &s_pk_bar[stg]);
+            };
+            if (tid == 0)
+                for (int j = 0; j < min(nmine, kPackStages - 1); ++j) {
+                    // a stage used by the previous pass must have been released by all warps before it is re-armed
+                    const int q = ring_it + j;
+                    if (q >= kPackStages) mbar_wait(&s_pk_empty[q % kPackStages], (uint32_t)(q / kPackStages - 1) & 1u);
+                    arm(j);
+                }
+            for (int j = 0; j < nmine; ++j) {
+                // Producer (thread 0): re-arm the stage tile j-1 used, once all kWarps warps have released it (per-stage
+                // "empty" mbarrier; no block-wide barrier per tile, so a warp waiting for its slot reservation does not
+                // hold up the other 15 -- they may run up to kPackStages-1 tiles ahead).
+                if (tid == 0 && j + kPackStages - 1 < nmine) {
+                    const int q = ring_it + j + kPackStages - 1;           // ring slot sequence number being armed
+                    if (q >= kPackStages) mbar_wait(&s_pk_empty[q % kPackStages], (uint32_t)(q / kPackStages - 1) & 1u);
+                    arm(j + kPackStages - 1);
+                }
+                const int qj = ring_it + j;
+                const int stg = qj % kPackStages;
+                mbar_wait(&s_pk_bar[stg], (uint32_t)(qj / kPackStages) & 1u);
+                const int base = (blockIdx.x + j * G) * kTileV;
+                float4 a[kPackTile];
+                bool in[kPackTile];
+#pragma unroll
+                for (int u = 0; u < kPackTile; ++u) {
+                    const int v = base + u * kThreads + tid;
+                    in[u] = v < n4;
+                    a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (in[u]) {
+                        a[u] = pk_r[stg * kTileV + u * kThreads + tid];
+                        if (!res_only) {
+                            const float4 gq = pk_g[stg * kTileV + u * kThreads + tid];
+                            a[u].x += gq.x; a[u].y += gq.y; a[u].z += gq.z; a[u].w += gq.w;
+                            st_stream_f4(r4 + v, a[u]);
+                        }
+                        if (attempt == 0) st_stream_f4(g4 + v, make_float4(0.f, 0.f, 0.f, 0.f));
+                    }
+                }
+                __syncwarp();                                               // the warp's part of the tile is in registers:
+                if (lane == 0) mbar_arrive(&s_pk_empty[stg]);               // release the stage (1 of kWarps arrivals)
+                // ---- selection: one slot reservation per (warp, trip, destination) ------------------------------
+                // 16 element flags per lane -> 16 ballots; the warp's trip covers 4 windows of 128 consecutive elements,
+                // which (regions being contiguous ranges) almost always belong to ONE destination, so the append costs
+                // one global atomic per trip instead of one per selected vector component.
+                unsigned msk[kPackTile * 4];
+                unsigned mybits = 0u;
+                int tot = 0;
 #pragma unroll
                 for (int u = 0; u < kPackTile; ++u) {
                     const float xs[4] = {a[u].x, a[u].y, a[u].z, a[u].w};
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        const int q = u * 4 + c;
-                        if ((mine >> q) & 1u) {
-                            const int pos = run + __popc(md[q] & lt);
-                            if (pos < cap) {
-                                sidx[pos] = 4 * (base + u * kThreads + tid) + c - off_d;
-                                sval[pos] = xs[c];
-                            } else {
-                                dropped++;
+                        const bool pred = in[u] && fabsf(xs[c]) > thr_sel;
+                        // TopkDSA zeroes the residual at the exact top-k INCLUDING the k-th element itself, which the
+                        // strict '>' select does not send (reference quirk): a rare, direct store
+                        if (p.residual_mode == RES_LOCAL_GE && in[u] && xs[c] != 0.f && fabsf(xs[c]) == thr_sel)
+                            p.res[4 * (base + u * kThreads + tid) + c] = 0.f;
+                        const unsigned m = __ballot_sync(0xffffffffu, pred);
+                        msk[u * 4 + c] = m;
+                        tot += __popc(m);
+                        if (pred) mybits |= 1u << (u * 4 + c);
+                    }
+                }
+                if (tot == 0) continue;
+                // guard ladder of my selected elements
+#pragma unroll
+                for (int u = 0; u < kPackTile; ++u) {
+                    const float xs[4] = {a[u].x, a[u].y, a[u].z, a[u].w};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (mybits & (1u << (u * 4 + c))) {
+                            const float ax = fabsf(xs[c]);
+                            gc[0]++;
+                            if (ladder_on) {
+#pragma unroll
+                                for (int j2 = 1; j2 < kGuardMax; ++j2) gc[j2] += (j2 <= p.guard_loops && ax > lad[j2]) ? 1 : 0;
                             }
                         }
-                        run += __popc(md[q]);
+                    }
+                }
+                const int e_first = 4 * (base + (warp << 5));
+                const int e_last = min(n - 1, 4 * (base + (kPackTile - 1) * kThreads + (warp << 5) + 31) + 3);
+                const int dlo = region_of(s_edges, P, e_first), dhi = region_of(s_edges, P, e_last);
+                for (int d = dlo; d <= dhi; ++d) {
+                    unsigned md[kPackTile * 4];
+                    unsigned mine = mybits;
+                    int cnt = 0;
+                    if (dlo == dhi) {
+#pragma unroll
+                        for (int q = 0; q < kPackTile * 4; ++q) { md[q] = msk[q]; cnt += __popc(md[q]); }
+                    } else {
+                        const int lo_d = s_edges[d], hi_d = s_edges[d + 1];
+                        mine = 0u;
+#pragma unroll
+                        for (int u = 0; u < kPackTile; ++u) {
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                const int i = 4 * (base + u * kThreads + tid) + c;
+                                const bool pd = ((mybits >> (u * 4 + c)) & 1u) && i >= lo_d && i < hi_d;
+                                md[u * 4 + c] = __ballot_sync(0xffffffffu, pd);
+                                cnt += __popc(md[u * 4 + c]);
+                                if (pd) mine |= 1u << (u * 4 + c);
+                            }
+                        }
+                    }
+                    if (cnt == 0) continue;
+                    int run = 0;
+                    if (lane == 0) run = atomicAdd(&st->send_cursor[d], cnt);
+                    run = __shfl_sync(0xffffffffu, run, 0);
+                    const int scap_d = s_soff[d + 1] - s_soff[d];
+                    int* sidx = my_sidx + s_soff[d];
+                    float* sval = my_sval + s_soff[d];
+                    const int off_d = s_edges[d];
+                    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+                    for (int u = 0; u < kPackTile; ++u) {
+                        const float xs[4] = {a[u].x, a[u].y, a[u].z, a[u].w};
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const int q = u * 4 + c;
+                            if ((mine >> q) & 1u) {
+                                const int pos = run + __popc(md[q] & lt);
+                                const int i = 4 * (base + u * kThreads + tid) + c;
+                                if (pos < scap_d) {
+                                    sidx[pos] = i - off_d;
+                                    sval[pos] = xs[c];
+                                    if (p.residual_mode != RES_OKTOPK) p.res[i] = 0.f;   // sent => cleared (classic rule)
+                                } else {
+                                    dropped++;                                           // stays in the residual
+                                }
+                            }
+                            run += __popc(md[q]);
+                        }
                     }
                 }
             }
-        }
-        if (blockIdx.x == 0 && warp == 0 && (n & 3)) {
-            int i = n4 * 4 + lane;
-            bool in = i < n;
-            float a = 0.f;
-            if (in) {
-                a = two_pass ? p.res[i] : (p.g[i] + p.res[i]);
-                if (!two_pass) p.res[i] = a;
-                p.g[i] = 0.f;
+            ring_it += nmine;
+            if (blockIdx.x == 0 && warp == 0 && (n & 3)) {
+                int i = n4 * 4 + lane;
+                bool in = i < n;
+                float a = 0.f;
+                if (in) {
+                    a = res_only ? p.res[i] : (p.g[i] + p.res[i]);
+                    if (!res_only) p.res[i] = a;
+                    p.g[i] = 0.f;
+                }
+                emit(i, a, in);
             }
-            emit(i, a, in);
-        }
-        if (p.residual_mode == RES_LOCAL_GE && blockIdx.x == 0 && (n & 3)) {      // scalar tail of the same rule
-            for (int i = n4 * 4 + tid; i < n; i += kThreads) {
-                float x = p.res[i];
-                if (x != 0.f && fabsf(x) == thr_sel) p.res[i] = 0.f;
+            if (p.residual_mode == RES_LOCAL_GE && blockIdx.x == 0 && (n & 3)) {      // scalar tail of the same rule
+                for (int i = n4 * 4 + tid; i < n; i += kThreads) {
+                    float x = p.res[i];
+                    if (x != 0.f && fabsf(x) == thr_sel) p.res[i] = 0.f;
+                }
             }
-        }
 #pragma unroll
-        for (int j = 0; j < kGuardMax; ++j) {
-            int c = warp_sum(gc[j]);
-            if (lane == 0 && c) atomicAdd(&st->guard_counts[j], c);
+            for (int j = 0; j < kGuardMax; ++j) {
+                int c = warp_sum(gc[j]);
+                if (lane == 0 && c) atomicAdd(&st->guard_counts[j], c);
+            }
+            if (!can_redo) break;
+            grid_sync(&st->bar);
+            bool over = false;
+            for (int d = 0; d < P; ++d) over = over || (__ldcg(&st->send_cursor[d]) > s_soff[d + 1] - s_soff[d]);
+            if (!over || attempt >= p.max_redo) break;
+            grid_sync(&st->bar);                                            // every CTA has read the cursors
+            if (blockIdx.x == 0 && tid == 0) {
+                for (int d = 0; d < P; ++d) st->send_cursor[d] = 0;
+                for (int q = 0; q < kGuardMax; ++q) st->guard_counts[q] = 0;
+                st->cum_redo += 1ULL;
+            }
+            thr_sel = fmaxf(thr_sel, 1e-30f) * redo_f;                      // identical on every CTA
+            redo_f = fminf(redo_f * redo_f, 1e6f);
+            ++attempt;
+            grid_sync(&st->bar);
         }
-        int dsum = warp_sum(dropped);
-        if (lane == 0 && dsum) atomicAdd(&st->stat_overflow_send, dsum);
-        if (PH_PACK + 1 < p.phase_end) grid_sync(&st->bar);
+        {
+            int dsum = warp_sum(dropped);
+            if (lane == 0 && dsum) atomicAdd(&st->cum_overflow_send, (unsigned long long)dsum);
+        }
+        // ---- publish: final (guarded) threshold + per-destination counts into the owners' mailboxes.  Done by the LAST CTA
+        //      to finish packing (ticket), or by block 0 when the redo policy's grid barrier has already run.
+        const bool publisher = can_redo ? (blockIdx.x == 0) : last_cta_ticket(&st->tick[0]);
+        if (publisher) {
+            if (tid == 0) {
+                float t = thr_sel;
+                int j = 0;
+                if (!two_pass)
+                    while (j < p.guard_loops && __ldcg(&st->guard_counts[j]) > p.guard_limit) { t *= p.guard_factor; ++j; }
+                const int cnt = __ldcg(&st->guard_counts[j]);
+                st->local_thr_used = t;
+                st->pack_thr = thr_sel;
+                st->stat_local_count = cnt;
+                float nt = t;
+                if ((double)cnt < p.l_low_cnt) nt = t / p.l_factor;
+                else if ((double)cnt > p.l_high_cnt) nt = t * p.l_factor;
+                st->local_thr = nt;
+                for (int q = 0; q < kGuardMax; ++q) st->guard_counts[q] = 0;
+                s_thr[0] = t;
+                __threadfence();
+            }
+            __syncthreads();
+            if (tid < P) {
+                const int c = min(__ldcg(&st->send_cursor[tid]), s_soff[tid + 1] - s_soff[tid]);
+                st_relaxed_sys_u32(reinterpret_cast<uint32_t*>(rs_thr(p.peers[tid], p.L, par, rank)), __float_as_uint(s_thr[0]));
+                st_release_sys_u64(rs_mbox(p.peers[tid], p.L, par, rank), make_mail(epoch, (uint32_t)c));
+            }
+            __syncthreads();
+        }
         stamp(1);
-    }
-
-    // ======================================================================== PH_PUBLISH_RS
-    if (p.phase_begin <= PH_PUBLISH_RS && PH_PUBLISH_RS < p.phase_end && blockIdx.x == 0) {
-        if (tid == 0) {
-            float t = two_pass ? st->local_thr_used : st->local_thr;
-            int j = 0;
-            if (!two_pass)
-                while (j < p.guard_loops && st->guard_counts[j] > p.guard_limit) { t *= p.guard_factor; ++j; }
-            const int cnt = st->guard_counts[j];
-            st->local_thr_used = t;
-            st->stat_local_count = cnt;
-            float nt = t;
-            if ((double)cnt < p.l_low_cnt) nt = t / p.l_factor;
-            else if ((double)cnt > p.l_high_cnt) nt = t * p.l_factor;
-            st->local_thr = nt;
-            for (int q = 0; q < kGuardMax; ++q) st->guard_counts[q] = 0;
-            s_thr[0] = t;
-        }
-        __syncthreads();
-        if (tid < P) {
-            const int c = min(st->send_cursor[tid], p.L.cap);
-            st->send_cursor[tid] = 0;
-            st_relaxed_sys_u32(reinterpret_cast<uint32_t*>(rs_thr(p.peers[tid], p.L, par, rank)), __float_as_uint(s_thr[0]));
-            st_release_sys_u64(rs_mbox(p.peers[tid], p.L, par, rank), make_mail(epoch, (uint32_t)c));
-        }
-        __syncthreads();
     }
 
     // ======================================================================== PH_REDUCE
     if (p.phase_begin <= PH_REDUCE && PH_REDUCE < p.phase_end) {
+        // All P mailboxes, my own included: the local publisher raises my own flag only after EVERY local CTA has finished
+        // packing (ticket), so this wait is also the local barrier between "bucket zeroed" and "contributions added".
         if (tid < P) {
-            s_cnt[tid] = (int)wait_mailbox(rs_mbox(me, p.L, par, tid), epoch, SpinGuard{&st->fault, p.timeout_ns, FAULT_RS_TIMEOUT});
+            s_cnt[tid] = (int)wait_mailbox(rs_mbox(me, p.L, par, tid), epoch, sg_rs);
             s_thr[tid] = __uint_as_float(ld_relaxed_sys_u32(reinterpret_cast<uint32_t*>(rs_thr(me, p.L, par, tid))));
         }
         __syncthreads();
+        stamp(6);
         const int off_me = s_edges[rank];
         const int len_me = s_edges[rank + 1] - off_me;
         float* greg = p.g + off_me;
@@ -577,21 +642,21 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
             }
             pulled++;
         };
+        const int my_soff = s_soff[rank];
         if (!p.deterministic) {
-            ChunkSrc srcs[OKT_MAXP];
-            float thr_of[OKT_MAXP];
-            for (int t = 0; t < P; ++t) {            // staggered start: spread the pulls over the switch ports
-                const int s = (rank + t) % P;
-                srcs[t].idx = send_idx(p.peers[s], p.L, P, par, rank);
-                srcs[t].val = send_val(p.peers[s], p.L, P, par, rank);
-                srcs[t].count = s_cnt[s];
-                thr_of[t] = s_thr[s];
+            if (tid < P) {                           // staggered start: spread the pulls over the switch ports
+                const int s = (rank + tid) % P;
+                s_srcs[tid].idx = send_idx_base(p.peers[s], p.L) + my_soff;
+                s_srcs[tid].val = send_val_base(p.peers[s], p.L) + my_soff;
+                s_srcs[tid].count = s_cnt[s];
+                s_sthr[tid] = s_thr[s];
             }
-            pull_chunks(srcs, P, p.pull_tma != 0, &s_pull, pipe_it,
-                        [&](int sl, int idx, float val) { add(sl, idx, val, thr_of); });
+            __syncthreads();
+            pull_chunks(s_srcs, P, p.pull_tma != 0, &s_pull, pipe_it,
+                        [&](int sl, int idx, float val) { add(sl, idx, val, s_sthr); });
         } else {
             for (int s = 0; s < P; ++s) {            // fixed source order => bitwise reproducible sums
-                ChunkSrc src{send_idx(p.peers[s], p.L, P, par, rank), send_val(p.peers[s], p.L, P, par, rank), s_cnt[s]};
+                ChunkSrc src{send_idx_base(p.peers[s], p.L) + my_soff, send_val_base(p.peers[s], p.L) + my_soff, s_cnt[s]};
                 float thr1 = s_thr[s];
                 pull_chunks(&src, 1, p.pull_tma != 0, &s_pull, pipe_it,
                             [&](int, int idx, float val) { add(0, idx, val, &thr1); });
@@ -604,14 +669,17 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
         stamp(2);
     }
 
-    // ======================================================================== PH_GSELECT
+    // ======================================================================== PH_GSELECT (+ publish my gather count)
     if (p.phase_begin <= PH_GSELECT && PH_GSELECT < p.phase_end) {
         const float gthr = st->global_thr;
         const int lo = s_edges[rank], hi = s_edges[rank + 1];
         const int gcap = p.L.gcap;
         int* gi = gat_idx(me, p.L, par);
         float* gv = gat_val(me, p.L, par);
-        const float fP = (float)P;
+        // GLB_ALL_NONZERO (TopkDSA): everything non-zero is gathered, so the reduced region is left IN PLACE (the final
+        // phase overwrites every entry with val/P; the dense-fallback path reads the regions directly).  The threshold
+        // modes claim the value and leave the bucket all-zero for the final phase.
+        const bool keep_in_place = p.global_mode == GLB_ALL_NONZERO;
         int dropped = 0;
         if (p.cand_mode) {
             // Low density: walk the candidate list of the reduce phase (every index of my region that received a
@@ -622,13 +690,13 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
             for (int c = gtid; c < ncr; c += gthreads) {
                 const bool in = c < ncand;
                 const int i = in ? __ldcg(p.cand + c) : 0;
-                const float v = in ? atomicExch(p.g + lo + i, 0.f) : 0.f;
+                const float v = in ? (keep_in_place ? __ldcg(p.g + lo + i) : atomicExch(p.g + lo + i, 0.f)) : 0.f;
                 const bool nz = in && v != 0.f;
                 const bool sel = (p.global_mode == GLB_THRESHOLD) ? (nz && fabsf(v) > gthr) : nz;
                 const int pos = warp_append(&st->gather_cursor, sel);
                 if (sel) {
                     if (pos < gcap) { gi[pos] = lo + i; gv[pos] = v; }
-                    else dropped++;
+                    else { dropped++; if (keep_in_place) p.g[lo + i] = 0.f; }
                 }
             }
         } else {
@@ -640,11 +708,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
                 const bool nz = in && v != 0.f;
                 const bool sel = (p.global_mode == GLB_THRESHOLD) ? (nz && fabsf(v) > gthr) : nz;
                 const int pos = warp_append(&st->gather_cursor, sel);
+                bool lost = false;
                 if (sel) {
                     if (pos < gcap) { gi[pos] = i; gv[pos] = v; }
-                    else dropped++;
+                    else { dropped++; lost = true; }
                 }
-                if (nz) p.g[i] = 0.f;
+                if (nz && (!keep_in_place || lost)) p.g[i] = 0.f;
             };
             const int first = min(hi, (lo + 3) & ~3), last = max(first, hi & ~3);
             if (blockIdx.x == 0 && warp == 0) {
@@ -655,7 +724,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
             const float4* gv4 = reinterpret_cast<const float4*>(p.g + first);
             tma_stream_tiles<kScanStages>(gv4, nv, dyn_pk, s_sc_bar, [&](const float4* tile, int q0) {
                 float4 a[kPackTile];
-                unsigned nzbits = 0u, selbits = 0u;
+                unsigned nzbits = 0u, selbits = 0u, lostbits = 0u;
                 int tot = 0;
 #pragma unroll
                 for (int u = 0; u < kPackTile; ++u) {
@@ -692,81 +761,147 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
                                 gv[pos] = xs[c];
                             } else {
                                 dropped++;
+                                lostbits |= 1u << (u * 4 + c);
                             }
                         }
                         run += __popc(m);
                     }
-                    if ((nzbits >> (u * 4)) & 0xfu)
-                        *reinterpret_cast<float4*>(p.g + first + 4 * (q0 + u * kThreads + tid)) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (!keep_in_place) {
+                        if ((nzbits >> (u * 4)) & 0xfu)
+                            *reinterpret_cast<float4*>(p.g + first + 4 * (q0 + u * kThreads + tid)) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    } else if ((lostbits >> (u * 4)) & 0xfu) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            if ((lostbits >> (u * 4 + c)) & 1u) p.g[first + 4 * (q0 + u * kThreads + tid) + c] = 0.f;
+                    }
                 }
             });
         }
-        (void)fP;
         int dsum = warp_sum(dropped);
-        if (lane == 0 && dsum) atomicAdd(&st->stat_overflow_gather, dsum);
-        if (PH_GSELECT + 1 < p.phase_end) grid_sync(&st->bar);
+        if (lane == 0 && dsum) atomicAdd(&st->cum_overflow_gather, (unsigned long long)dsum);
         stamp(3);
-    }
-
-    // ======================================================================== PH_PUBLISH_AG
-    if (p.phase_begin <= PH_PUBLISH_AG && PH_PUBLISH_AG < p.phase_end && blockIdx.x == 0) {
-        if (tid == 0) s_misc[0] = min(st->gather_cursor, p.L.gcap);
-        __syncthreads();
-        if (tid < P) st_release_sys_u64(ag_mbox(p.peers[tid], p.L, par, rank), make_mail(epoch, (uint32_t)s_misc[0]));
-        __syncthreads();
-        if (tid == 0) { st->gather_cursor = 0; st->cand_cursor = 0; }
+        // publish my gather count: the last CTA to finish the selection does it (no grid barrier)
+        if (last_cta_ticket(&st->tick[1])) {
+            if (tid == 0) s_misc[0] = min(__ldcg(&st->gather_cursor), p.L.gcap);
+            __syncthreads();
+            if (tid < P) st_release_sys_u64(ag_mbox(p.peers[tid], p.L, par, rank), make_mail(epoch, (uint32_t)s_misc[0]));
+            __syncthreads();
+        }
     }
 
     // ======================================================================== PH_FINAL
     if (p.phase_begin <= PH_FINAL && PH_FINAL < p.phase_end) {
-        if (tid < P) s_cnt[tid] = (int)wait_mailbox(ag_mbox(me, p.L, par, tid), epoch, SpinGuard{&st->fault, p.timeout_ns, FAULT_AG_TIMEOUT});
+        // (again all P flags including my own = local barrier: every local CTA has finished the global selection)
+        if (tid < P) s_cnt[tid] = (int)wait_mailbox(ag_mbox(me, p.L, par, tid), epoch, sg_ag);
         __syncthreads();
+        stamp(7);
         int T = 0;
         for (int s = 0; s < P; ++s) T += s_cnt[s];
-        float gsel = 0.f;
-        if (p.global_mode == GLB_EXACT_TOPK) {
-            Seg segs[OKT_MAXP];
-            for (int s = 0; s < P; ++s) { segs[s].ptr = gat_val(p.peers[s], p.L, par); segs[s].count = s_cnt[s]; segs[s].idx = nullptr; }
-            const uint32_t kk = (uint32_t)min(T, p.k);
-            gsel = (kk > 0) ? grid_kth_abs(segs, P, true, kk, st, s_hist, s_w, 0) : 0.f;
-            if (blockIdx.x == 0 && tid == 0) st->global_thr = gsel;
-        } else if (p.global_mode == GLB_THRESHOLD && blockIdx.x == 0 && tid == 0) {
-            float gt = st->global_thr;
-            if ((double)T < p.g_low_cnt) gt = gt / p.g_inc;
-            else if ((double)T > p.g_high_cnt) gt = gt * p.g_dec;
-            st->global_thr = gt;
-        }
-        const float thr_used = st->local_thr_used;
         const float fP = (float)P;
-        ChunkSrc srcs[OKT_MAXP];
-        int src_rank[OKT_MAXP];
-        for (int t = 0; t < P; ++t) {
-            const int s = (rank + t) % P;
-            srcs[t].idx = gat_idx(p.peers[s], p.L, par);
-            srcs[t].val = gat_val(p.peers[s], p.L, par);
-            srcs[t].count = s_cnt[s];
-            src_rank[t] = s;
-        }
+        const bool dense_path = p.global_mode == GLB_ALL_NONZERO && p.dense_nnz_limit > 0 && T >= p.dense_nnz_limit &&
+                                P > 1 && p.peer_g[0] != nullptr;
         int kept_cnt = 0;
-        const bool exact = p.global_mode == GLB_EXACT_TOPK;
-        pull_chunks(srcs, P, p.pull_tma != 0, &s_pull, pipe_it, [&](int sl, int idx, float val) {
-            if ((unsigned)idx >= (unsigned)n) return;
-            bool keep = exact ? (fabsf(val) >= gsel) : true;
-            if (!keep) return;
-            kept_cnt++;
-            p.g[idx] = val / fP;             // the bucket is all-zero here: every kept entry (own region included) lands now
-            if (p.residual_mode == RES_OKTOPK) {
-                float r = p.res[idx];
-                if (fabsf(r) > thr_used) p.res[idx] = 0.f;
+        if (dense_path) {
+            // TopkDSA's dynamic dense fallback (reference VGG/allreducer.py:1311-1353: when the reduced regions hold
+            // >= n/3 non-zeros the index/value lists would be bigger than the regions themselves): every rank copies
+            // every peer's reduced region straight out of that peer's bucket (128-bit peer loads), scaled by 1/P.
+            // My own region must stay un-scaled until every peer has read it: "done reading" flags, then scale in place.
+            const float inv = 1.f / fP;
+            for (int t = 1; t < P; ++t) {
+                const int s = (rank + t) % P;
+                const int lo_s = s_edges[s], hi_s = s_edges[s + 1];
+                const float* src = p.peer_g[s];
+                const int first = min(hi_s, (lo_s + 3) & ~3), last = max(first, hi_s & ~3);
+                for (int i = lo_s + gtid; i < first; i += gthreads) p.g[i] = ld_peer_f32(src + i) * inv;
+                for (int i = last + gtid; i < hi_s; i += gthreads) p.g[i] = ld_peer_f32(src + i) * inv;
+                const int nv = (last - first) >> 2;
+                const int4* s4 = reinterpret_cast<const int4*>(src + first);
+                float4* d4 = reinterpret_cast<float4*>(p.g + first);
+                for (int v = gtid; v < nv; v += gthreads) {
+                    const int4 r = ld_peer_i4(s4 + v);
+                    st_stream_f4(d4 + v, make_float4(__int_as_float(r.x) * inv, __int_as_float(r.y) * inv,
+                                                     __int_as_float(r.z) * inv, __int_as_float(r.w) * inv));
+                }
             }
-        });
-        int ksum = warp_sum(kept_cnt);
-        if (lane == 0 && ksum) atomicAdd(&st->stat_global_count, ksum);
-        grid_sync(&st->bar);
-        if (blockIdx.x == 0 && tid == 0) {
+            grid_sync(&st->bar);                     // all my peer reads have returned
+            if (blockIdx.x == 0 && tid < P) st_release_sys_u64(done_mbox(p.peers[tid], p.L, par, rank), make_mail(epoch, 1u));
+            if (tid < P) wait_mailbox(done_mbox(me, p.L, par, tid), epoch, sg_done);
+            __syncthreads();
+            const int lo = s_edges[rank], hi = s_edges[rank + 1];
+            for (int i = lo + gtid; i < hi; i += gthreads) p.g[i] = __ldcg(p.g + i) * inv;
+            if (blockIdx.x == 0 && tid == 0) { st->stat_dense_fallback = 1; st->stat_global_count = T; }
+        } else {
+            float gsel = 0.f;
+            if (p.global_mode == GLB_EXACT_TOPK) {
+                if (tid < P) { s_segs[tid].ptr = gat_val(p.peers[tid], p.L, par); s_segs[tid].count = s_cnt[tid]; s_segs[tid].idx = nullptr; }
+                __syncthreads();
+                const uint32_t kk = (uint32_t)min(T, p.k);
+                gsel = (kk > 0) ? grid_kth_abs(s_segs, P, true, kk, st, s_hist, s_w, 0) : 0.f;
+                if (blockIdx.x == 0 && tid == 0) st->global_thr = gsel;
+            } else if (p.global_mode == GLB_THRESHOLD && blockIdx.x == 0 && tid == 0) {
+                float gt = st->global_thr;
+                if ((double)T < p.g_low_cnt) gt = gt / p.g_inc;
+                else if ((double)T > p.g_high_cnt) gt = gt * p.g_dec;
+                st->global_thr = gt;
+            }
+            const float thr_used = st->local_thr_used;
+            if (tid < P) {
+                const int s = (rank + tid) % P;
+                s_srcs[tid].idx = gat_idx(p.peers[s], p.L, par);
+                s_srcs[tid].val = gat_val(p.peers[s], p.L, par);
+                s_srcs[tid].count = s_cnt[s];
+            }
+            __syncthreads();
+            const bool exact = p.global_mode == GLB_EXACT_TOPK;
+            pull_chunks(s_srcs, P, p.pull_tma != 0, &s_pull, pipe_it, [&](int sl, int idx, float val) {
+                if ((unsigned)idx >= (unsigned)n) return;
+                bool keep = exact ? (fabsf(val) >= gsel) : true;
+                if (!keep) return;
+                kept_cnt++;
+                p.g[idx] = val / fP;             // the bucket is all-zero here: every kept entry (own region included) lands now
+                if (p.residual_mode == RES_OKTOPK) {
+                    float r = p.res[idx];
+                    if (fabsf(r) > thr_used) p.res[idx] = 0.f;
+                }
+            });
+            int ksum = warp_sum(kept_cnt);
+            if (lane == 0 && ksum) atomicAdd(&st->stat_global_count, ksum);
+        }
+        // end of call: the last CTA to get here closes the books (no grid barrier: everybody else just exits)
+        if (last_cta_ticket(&st->tick[2]) && tid == 0) {
+            const unsigned long long t_end = globaltimer_ns();
             st->epoch = epoch;
-            st->t_phase[4] = globaltimer_ns();
+            st->t_phase[4] = t_end;
             st->stat_gather_total = T;
+            for (int d = 0; d < P; ++d) st->send_cursor[d] = 0;
+            st->gather_cursor = 0;
+            st->cand_cursor = 0;
+            const unsigned long long os = *reinterpret_cast<volatile unsigned long long*>(&st->cum_overflow_send);
+            const unsigned long long og = *reinterpret_cast<volatile unsigned long long*>(&st->cum_overflow_gather);
+            const unsigned long long rd = *reinterpret_cast<volatile unsigned long long*>(&st->cum_redo);
+            st->stat_overflow_send = (int)min(os - st->snap_overflow_send, 0x7fffffffULL);
+            st->stat_overflow_gather = (int)min(og - st->snap_overflow_gather, 0x7fffffffULL);
+            st->stat_redo = (int)(rd - st->snap_redo);
+            st->snap_overflow_send = os; st->snap_overflow_gather = og; st->snap_redo = rd;
+            TraceRec& tr = st->trace[epoch % kTraceLen];
+            auto us = [&](int a, int b) {
+                const unsigned long long ta = *reinterpret_cast<volatile unsigned long long*>(&st->t_phase[a]);
+                const unsigned long long tb = *reinterpret_cast<volatile unsigned long long*>(&st->t_phase[b]);
+                return tb >= ta ? (float)(tb - ta) * 1e-3f : 0.f;
+            };
+            tr.epoch = epoch;
+            tr.local_count = st->stat_local_count;
+            tr.global_count = *reinterpret_cast<volatile int*>(&st->stat_global_count);
+            tr.recv_total = *reinterpret_cast<volatile int*>(&st->stat_recv_total);
+            tr.gather_total = T;
+            tr.overflow_send = st->stat_overflow_send;
+            tr.overflow_gather = st->stat_overflow_gather;
+            tr.redo = st->stat_redo;
+            tr.local_thr = st->local_thr_used;
+            tr.global_thr = st->global_thr;
+            tr.us_local = us(5, 0); tr.us_pack = us(0, 1); tr.us_wait_rs = us(1, 6); tr.us_reduce = us(6, 2);
+            tr.us_gselect = us(2, 3); tr.us_wait_ag = us(3, 7); tr.us_final = us(7, 4);
+            tr.t_begin = st->t_phase[5];
         }
     }
 }

@@ -15,7 +15,11 @@ __global__ void __launch_bounds__(kOptThreads) fused_sgd_kernel(float* __restric
                                                                  float* __restrict__ mom, int n, float lr,
                                                                  float momentum, float dampening, float wd,
                                                                  int nesterov, int first, int zero_grad,
-                                                                 float grad_scale, const float* __restrict__ lr_ptr) {
+                                                                 float grad_scale, const float* __restrict__ lr_ptr,
+                                                                 const int* __restrict__ fault) {
+    // a bounded cross-GPU wait timed out inside the reduction of this bucket: the gradient is partial, do NOT apply it
+    // (the host sees the mirrored fault flag at its next step() and re-synchronises the replicas)
+    if (fault != nullptr && *reinterpret_cast<const volatile int*>(fault) != 0) return;
     if (lr_ptr) lr = *lr_ptr;            // device-resident learning rate: the launch is CUDA-graph replayable
     const int n4 = n >> 2;
     float4* p4 = reinterpret_cast<float4*>(p);
@@ -55,7 +59,9 @@ __global__ void __launch_bounds__(kOptThreads) fused_bert_adam_kernel(float* __r
                                                                        float* __restrict__ m, float* __restrict__ v,
                                                                        int n, float lr, float b1, float b2, float eps,
                                                                        float wd, int zero_grad,
-                                                                       const float* __restrict__ lr_ptr) {
+                                                                       const float* __restrict__ lr_ptr,
+                                                                       const int* __restrict__ fault) {
+    if (fault != nullptr && *reinterpret_cast<const volatile int*>(fault) != 0) return;
     if (lr_ptr) lr = *lr_ptr;
     const int n4 = n >> 2;
     float4* p4 = reinterpret_cast<float4*>(p);
@@ -131,17 +137,59 @@ static inline int opt_grid(int n) {
 
 cudaError_t launch_fused_sgd(float* p, float* g, float* mom, int n, float lr, float momentum, float dampening,
                              float weight_decay, int nesterov, int first_step, int zero_grad, float grad_scale,
-                             const float* lr_ptr, cudaStream_t stream) {
+                             const float* lr_ptr, const int* fault, cudaStream_t stream) {
     fused_sgd_kernel<<<opt_grid(n), kOptThreads, 0, stream>>>(p, g, mom, n, lr, momentum, dampening, weight_decay,
-                                                             nesterov, first_step, zero_grad, grad_scale, lr_ptr);
+                                                             nesterov, first_step, zero_grad, grad_scale, lr_ptr, fault);
     return cudaGetLastError();
 }
 
 cudaError_t launch_fused_bert_adam(float* p, float* g, float* m, float* v, int n, float lr, float b1, float b2,
                                    float eps, float weight_decay, int zero_grad, const float* lr_ptr,
-                                   cudaStream_t stream) {
+                                   const int* fault, cudaStream_t stream) {
     fused_bert_adam_kernel<<<opt_grid(n), kOptThreads, 0, stream>>>(p, g, m, v, n, lr, b1, b2, eps, weight_decay,
-                                                                   zero_grad, lr_ptr);
+                                                                   zero_grad, lr_ptr, fault);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Multi-tensor gradient landing.  Autograd hands every parameter its gradient in a freshly allocated tensor; the
+// bucket the communication kernels work on is one flat symmetric allocation.  Instead of letting autograd
+// accumulate into pre-existing bucket views (one elementwise add kernel PER PARAMETER per step: 54 launches for
+// VGG-16) the gradients of a whole bucket are copied in by ONE launch: the kernel receives the (pointer, offset,
+// length) table by value, CTAs are dealt to tensors proportionally to their size.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kLandThreads = 256;
+constexpr int kLandPerCta = 8192;     // floats per CTA
+
+__global__ void __launch_bounds__(kLandThreads) land_kernel(const LandParams lp, float* __restrict__ bucket) {
+    // which tensor does this CTA work on?  (binary search over the CTA prefix table)
+    int lo = 0, hi = lp.count - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if ((int)blockIdx.x >= lp.blk_begin[mid]) lo = mid; else hi = mid - 1;
+    }
+    const int t = lo;
+    const int part = blockIdx.x - lp.blk_begin[t];
+    const float* __restrict__ src = lp.src[t];
+    float* __restrict__ dst = bucket + lp.dst_off[t];
+    const int numel = lp.numel[t];
+    const int begin = part * kLandPerCta;
+    const int end = min(numel, begin + kLandPerCta);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0;
+    if (aligned) {
+        const int v0 = begin >> 2, v1 = end >> 2;
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        for (int v = v0 + threadIdx.x; v < v1; v += kLandThreads) st_stream_f4(d4 + v, ld_stream_f4(s4 + v));
+        for (int i = (v1 << 2) + threadIdx.x; i < end; i += kLandThreads) dst[i] = src[i];
+    } else {
+        for (int i = begin + threadIdx.x; i < end; i += kLandThreads) dst[i] = src[i];
+    }
+}
+
+cudaError_t launch_land(const LandParams& lp, float* bucket, cudaStream_t stream) {
+    if (lp.count <= 0) return cudaSuccess;
+    land_kernel<<<lp.blk_begin[lp.count], kLandThreads, 0, stream>>>(lp, bucket);
     return cudaGetLastError();
 }
 

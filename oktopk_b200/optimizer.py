@@ -65,10 +65,16 @@ class _BucketedComm:
         self._hook_handles = []
         self._comm_stream = None
         self._use_streams = False
+        # Gradient landing: autograd produces every gradient in a fresh tensor; ONE multi-tensor kernel per bucket copies
+        # them into the flat symmetric bucket when the bucket's last gradient is ready (instead of autograd accumulating
+        # into pre-existing bucket views = one elementwise add kernel per parameter per step).
+        self._land = False
         for b in self._buckets:
             dev = b.params[0].device
             grad = allreducer.register_bucket(b.name, b.numel, dev)
             attach(b, grad, flatten_params)
+            if dev.type == "cuda" and self._cfg.land_grads and ext.available():
+                self._land = True
             b.pending = len(b.params)
             b.dirty = False                       # freshly zeroed
             if dev.type == "cuda":
@@ -139,10 +145,32 @@ class _BucketedComm:
             self._launch(self._buckets[self._next_launch])
             self._next_launch += 1
 
+    def _land_bucket(self, b: Bucket) -> None:
+        """Copy the autograd-produced gradients of bucket ``b`` into the flat bucket with one kernel launch and re-point
+        ``p.grad`` at the bucket views (what the user sees after ``synchronize()`` is the reduced gradient)."""
+        srcs, offs, numels = [], [], []
+        for p, o, v in zip(b.params, b.offsets, b.grad_views):
+            g = p.grad
+            if g is None:
+                v.zero_()                         # parameter unused in this step
+            elif g.data_ptr() == v.data_ptr():
+                continue                          # already accumulated in place (gradients were never detached)
+            elif g.dtype == torch.float32 and g.is_cuda and g.stride() == v.stride():
+                srcs.append(g.data_ptr())
+                offs.append(o)
+                numels.append(g.numel())
+            else:
+                v.copy_(g)
+            p.grad = v
+        if srcs:
+            ext.require().land_grads(srcs, offs, numels, b.grad.data_ptr(), torch.cuda.current_stream().cuda_stream)
+
     def _launch(self, b: Bucket) -> None:
         if b.launched:
             return
         b.launched = True
+        if self._land:
+            self._land_bucket(b)
         if self.momentum_correction:
             self._apply_momentum_correction(b)
         if self._comm_stream is not None:
@@ -188,8 +216,17 @@ class _BucketedComm:
             b.launched = False
         self._next_launch = 0
         self._synced = False
+        self._allreducer.poll_faults()           # pinned host flag, no sync: a timed-out peer wait surfaces at once
 
     def zero_grad(self, set_to_none: bool = False) -> None:  # noqa: ARG002 - views must survive
+        if self._land:
+            # detach the gradients from the bucket: the next backward hands every parameter a fresh tensor, which the
+            # landing kernel copies in (the bucket itself is overwritten, never accumulated into: no memset either)
+            for b in self._buckets:
+                for p in b.params:
+                    p.grad = None
+                b.dirty = False
+            return
         for b in self._buckets:
             if b.dirty:
                 b.grad.zero_()
@@ -235,8 +272,10 @@ class _BucketedComm:
                 m = 0.0                            # momentum already applied before communication
             if use_kernel:
                 ext.require().fused_sgd(b.flat_param.data_ptr() + 4 * s, b.grad.data_ptr() + 4 * s,
-                                        mom.data_ptr() + 4 * s, e - s, lr, m, damp, wd, int(nest), int(first), 1, 1.0,
-                                        torch.cuda.current_stream().cuda_stream, self._lr_ptr(gi))
+                                        mom.data_ptr() + 4 * s, e - s, lr, m, damp, wd, int(nest), int(first),
+                                        0 if self._land else 1, 1.0,
+                                        torch.cuda.current_stream().cuda_stream, self._lr_ptr(gi),
+                                        self._allreducer.fault_ptr(b.name))
             else:
                 gs, ms = b.grad[s:e], mom[s:e]
                 if b.flat_param is not None:
@@ -478,8 +517,9 @@ class BertAdam(_BucketedComm, torch.optim.Optimizer):
             if use_kernel:
                 ext.require().fused_bert_adam(b.flat_param.data_ptr() + 4 * s, b.grad.data_ptr() + 4 * s,
                                               m.data_ptr() + 4 * s, v.data_ptr() + 4 * s, e - s, lr, g["b1"], g["b2"],
-                                              g["e"], g["weight_decay"], 1, torch.cuda.current_stream().cuda_stream,
-                                              self._lr_ptr(gi))
+                                              g["e"], g["weight_decay"], 0 if self._land else 1,
+                                              torch.cuda.current_stream().cuda_stream,
+                                              self._lr_ptr(gi), self._allreducer.fault_ptr(b.name))
             else:
                 gs, ms, vs = b.grad[s:e], m[s:e], v[s:e]
                 ms.mul_(g["b1"]).add_(gs, alpha=1 - g["b1"])

@@ -32,13 +32,37 @@ class Bucket:
     group_slices: List[Tuple[int, int, int]] = field(default_factory=list)   # (group index, start, end)
     grad: Optional[torch.Tensor] = None
     flat_param: Optional[torch.Tensor] = None
+    grad_views: Optional[List[torch.Tensor]] = None
     pending: int = 0
     launched: bool = False
     dirty: bool = True
     event: Optional["torch.cuda.Event"] = None
 
     def views(self, flat: torch.Tensor) -> List[torch.Tensor]:
-        return [flat[o:o + p.numel()].view_as(p) for p, o in zip(self.params, self.offsets)]
+        """Per-parameter aliases of a flat buffer with the PARAMETER'S OWN memory layout: a channels_last conv weight
+        gets a channels_last view, so flat parameters, gradients and optimizer state stay element-wise aligned whatever
+        the layout (the flat kernels are element-wise, the sparse allreduce is permutation-agnostic)."""
+        out = []
+        for p, o in zip(self.params, self.offsets):
+            sl = flat[o:o + p.numel()]
+            if p.is_contiguous() or not _dense_non_overlapping(p):
+                out.append(sl.view_as(p))
+            else:
+                out.append(sl.as_strided(p.size(), p.stride()))
+        return out
+
+
+def _dense_non_overlapping(t: torch.Tensor) -> bool:
+    """True if the tensor's elements occupy exactly numel() consecutive storage slots (any permutation of dims)."""
+    if t.numel() <= 1:
+        return True
+    dims = sorted(((st, sz) for st, sz in zip(t.stride(), t.size()) if sz > 1))
+    expect = 1
+    for st, sz in dims:
+        if st != expect:
+            return False
+        expect *= sz
+    return True
 
 
 def _align(x: int) -> int:
@@ -97,5 +121,6 @@ def attach(bucket: Bucket, grad_flat: torch.Tensor, flatten_params: bool) -> Non
                 v.copy_(p.data)
                 p.data = v
             bucket.flat_param = fp
-        for p, v in zip(bucket.params, bucket.views(grad_flat)):
+        bucket.grad_views = bucket.views(grad_flat)
+        for p, v in zip(bucket.params, bucket.grad_views):
             p.grad = v

@@ -75,11 +75,13 @@ class MetricsWriter:
         if log_dir and rank == 0:
             os.makedirs(log_dir, exist_ok=True)
             self.f = open(os.path.join(log_dir, "metrics.jsonl"), "a")
-            try:
-                from torch.utils.tensorboard import SummaryWriter  # noqa: WPS433
-                self.tb = SummaryWriter(log_dir)
-            except Exception:  # noqa: BLE001
-                self.tb = None
+            from . import settings
+            if settings.TENSORBOARD:                  # OKTOPK_TENSORBOARD=1 (VGG/settings.py TENSORBOARD)
+                try:
+                    from torch.utils.tensorboard import SummaryWriter  # noqa: WPS433
+                    self.tb = SummaryWriter(log_dir)
+                except Exception:  # noqa: BLE001
+                    self.tb = None
 
     def add_scalars(self, tag: str, scalars: Dict[str, float], step: int) -> None:
         if self.f is not None:

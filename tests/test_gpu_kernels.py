@@ -188,3 +188,181 @@ def test_dense_path_matches_torch_sgd_on_gpu():
     for a, b in zip(net.parameters(), ref.parameters()):
         torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5)
     o.close()
+
+
+# ======================================================================================================
+# round 2: lossless exchange, overflow policy, conservation, new native schemes
+# ======================================================================================================
+def _scale(it):
+    """Gradient-scale jumps (x10, x100): the carried thresholds become far too small, the stale-threshold
+    iterations select a large part of the bucket."""
+    return 1.0 if it < 3 else (10.0 if it < 6 else 100.0)
+
+
+def _conservation_run(name, n, iters, cfg, exact_tol=0):
+    """P=1: after every call  acc (= grad + residual before) == residual after + result, element-wise and exactly:
+    whatever is not delivered stays in the residual."""
+    from oktopk_b200.parallel.gpu_engine import CudaBucketEngine
+    from oktopk_b200.parallel.world import World
+    eng = CudaBucketEngine(n, cfg, World(), name="t")
+    res_prev = torch.zeros(n)
+    hist = []
+    for it in range(iters):
+        g = torch.Generator().manual_seed(991 * it + 3)
+        x = torch.randn(n, generator=g) * _scale(it)
+        acc = (x.cuda() + res_prev.cuda()).cpu()
+        eng.grad.copy_(x.cuda())
+        eng.reduce(name)
+        torch.cuda.synchronize()
+        out, res, st = eng.grad.cpu(), eng.residual.cpu(), eng.stats()
+        bad = int((acc != res + out).sum())
+        assert bad <= exact_tol, "%s it %d: %d elements not conserved (stats %s)" % (name, it, bad, st)
+        assert st["fault"] == 0
+        hist.append(st)
+        res_prev = res
+    eng.close()
+    return hist
+
+
+def test_lossless_slots_never_drop_under_scale_jumps():
+    from oktopk_b200.config import OkTopkConfig
+    cfg = OkTopkConfig(density=0.01, local_recompute_interval=8, global_recompute_interval=8, repartition_interval=8)
+    hist = _conservation_run("oktopk", 400_003, 12, cfg)
+    assert all(h["lossless"] for h in hist)
+    assert all(h["overflow_send"] == 0 and h["overflow_gather"] == 0 and h["redo"] == 0 for h in hist), hist
+    assert max(h["local_count"] for h in hist) > 10 * 4000          # the stale threshold really over-selected
+
+
+def test_bounded_slots_redo_policy_is_lossless_and_conserved():
+    """slot_factor=1: the send slot holds ~k entries; after a x10 gradient-scale jump the stale threshold selects most
+    of the bucket.  The in-kernel policy raises the threshold and redoes the pack: nothing is dropped, nothing is lost."""
+    from oktopk_b200.config import OkTopkConfig
+    cfg = OkTopkConfig(density=0.01, local_recompute_interval=8, global_recompute_interval=8, repartition_interval=8,
+                       slot_factor=1.0, gather_factor=64.0)
+    hist = _conservation_run("oktopk", 400_003, 12, cfg)
+    assert not hist[0]["lossless"]
+    assert all(h["overflow_send"] == 0 for h in hist), [h["overflow_send"] for h in hist]
+    assert sum(h["redo"] for h in hist) > 0, "the overflow policy never ran"
+    assert all(h["local_count"] <= h["cap"] for h in hist)
+
+
+def test_bounded_gather_slot_overflow_is_conserved():
+    from oktopk_b200.config import OkTopkConfig
+    cfg = OkTopkConfig(density=0.01, local_recompute_interval=8, global_recompute_interval=8, repartition_interval=8,
+                       slot_factor=0.0, gather_factor=1.0)
+    hist = _conservation_run("oktopk", 400_003, 10, cfg)
+    assert sum(h["overflow_gather"] for h in hist) > 0            # entries were dropped from the gather slot ...
+    # ... and _conservation_run has checked that every one of them is still in the residual
+
+
+@pytest.mark.parametrize("name,tol", [("gaussiankSA", 0), ("topkDSA", 1)])
+def test_classic_residual_schemes_keep_unsent_entries(name, tol):
+    """TopkDSA / gaussiankSA zero the residual at the selection: with a too-small send slot the entries that found no
+    room must stay in the residual (round-1 bug: they were zeroed before the capacity check).  TopkDSA's reference
+    quirk (the k-th element itself is cleared but not sent) accounts for one element."""
+    from oktopk_b200.config import OkTopkConfig
+    cfg = OkTopkConfig(density=0.05, slot_factor=0.05, compressor=name)
+    hist = _conservation_run(name, 400_003, 4, cfg, exact_tol=tol)
+    assert all(h["overflow_send"] > 0 for h in hist), [h["overflow_send"] for h in hist]
+
+
+@pytest.mark.parametrize("slot_factor", [0.0, 64.0])
+def test_oktopk_matches_oracle_in_both_slot_layouts(slot_factor):
+    from oktopk_b200.config import OkTopkConfig
+    cfg = OkTopkConfig(density=0.01, local_recompute_interval=4, global_recompute_interval=4, repartition_interval=8,
+                       slot_factor=slot_factor, gather_factor=slot_factor)
+    _run_engine_vs_oracle("oktopk", 1_000_003, 10, cfg)
+
+
+@pytest.mark.parametrize("name", ["topkA2", "gtopk"])
+def test_native_reselect_and_tree_schemes_single_gpu(name):
+    from oktopk_b200.config import OkTopkConfig
+    _run_engine_vs_oracle(name, 300_001, 4, OkTopkConfig(density=0.01))
+
+
+@pytest.mark.parametrize("name", ["topkA", "topkA2", "gtopk"])
+def test_norm_clip_on_the_cuda_path(name):
+    """VGG/allreducer.py:1372-1379: the incoming gradient is scaled to L2 norm sqrt(1/P)*norm_clip inside the kernel."""
+    from oktopk_b200.config import OkTopkConfig
+    _run_engine_vs_oracle(name, 200_000, 3, OkTopkConfig(density=0.01, norm_clip=5.0), tol_count=8)
+
+
+def test_land_grads_kernel_copies_every_tensor():
+    C = _C()
+    torch.manual_seed(1)
+    sizes = [1, 3, 64, 1000, 8192, 8193, 100_003, 2_359_296] + [17] * 120        # > LAND_MAX tensors: several launches
+    srcs = [torch.randn(s, device="cuda") for s in sizes]
+    offs, o = [], 0
+    for s in sizes:
+        offs.append(o)
+        o += (s + 63) // 64 * 64
+    bucket = torch.full((o,), -7.0, device="cuda")
+    C.land_grads([t.data_ptr() for t in srcs], offs, sizes, bucket.data_ptr(), _stream())
+    torch.cuda.synchronize()
+    for t, off, s in zip(srcs, offs, sizes):
+        assert torch.equal(bucket[off:off + s], t)
+    touched = torch.zeros(o, dtype=torch.bool, device="cuda")
+    for off, s in zip(offs, sizes):
+        touched[off:off + s] = True
+    assert bool((bucket[~touched] == -7.0).all())                   # gaps untouched
+
+
+def test_gradient_landing_matches_accumulating_into_views():
+    """The landing path (fresh autograd gradients + one multi-tensor copy per bucket) must train exactly like the
+    round-1 path (autograd accumulating into bucket views), including a channels_last model."""
+    import copy
+    import oktopk_b200 as okt
+    from oktopk_b200.models import create_net
+    torch.manual_seed(0)
+    torch.backends.cudnn.deterministic = True
+    base, _ = create_net(10, "vgg16")
+    base = base.cuda().to(memory_format=torch.channels_last)
+    nets = [copy.deepcopy(base), copy.deepcopy(base)]
+    opts = []
+    for net, land in zip(nets, (True, False)):
+        cfg = okt.preset("vgg16", density=0.01, warmup_iters=1, land_grads=land)
+        opts.append(okt.DistributedOptimizer(torch.optim.SGD(net.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4),
+                                             named_parameters=net.named_parameters(), compression=okt.compressors["oktopk"],
+                                             is_sparse=True, cfg=cfg))
+    assert opts[0]._land and not opts[1]._land
+    for it in range(4):
+        x = torch.randn(8, 3, 32, 32, device="cuda").contiguous(memory_format=torch.channels_last)
+        y = torch.randint(0, 10, (8,), device="cuda")
+        for net, opt in zip(nets, opts):
+            opt.zero_grad()
+            torch.nn.functional.cross_entropy(net(x), y).backward()
+            opt.step()
+    torch.cuda.synchronize()
+    for a, b in zip(nets[0].parameters(), nets[1].parameters()):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
+    for o in opts:
+        o.close()
+
+
+def test_trace_ring_records_every_call():
+    from oktopk_b200.config import OkTopkConfig
+    from oktopk_b200.parallel.gpu_engine import CudaBucketEngine
+    from oktopk_b200.parallel.world import World
+    eng = CudaBucketEngine(200_000, OkTopkConfig(density=0.01), World(), name="t")
+    for it in range(5):
+        eng.grad.normal_()
+        eng.reduce("oktopk")
+    torch.cuda.synchronize()
+    tr = eng.trace()
+    assert [r["epoch"] for r in tr] == [1, 2, 3, 4, 5]
+    assert all(r["us_pack"] > 0 and r["local_count"] > 0 for r in tr), tr
+    eng.close()
+
+
+def test_fused_update_is_skipped_when_the_bucket_faulted():
+    C = _C()
+    n = 10_000
+    p = torch.ones(n, device="cuda"); g = torch.ones(n, device="cuda"); mom = torch.zeros(n, device="cuda")
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    C.fused_sgd(p.data_ptr(), g.data_ptr(), mom.data_ptr(), n, 0.1, 0.0, 0.0, 0.0, 0, 1, 0, 1.0, _stream(), 0, flag.data_ptr())
+    torch.cuda.synchronize()
+    assert float(p[0]) == pytest.approx(0.9)
+    flag.fill_(1)
+    C.fused_sgd(p.data_ptr(), g.data_ptr(), mom.data_ptr(), n, 0.1, 0.0, 0.0, 0.0, 0, 0, 0, 1.0, _stream(), 0, flag.data_ptr())
+    torch.cuda.synchronize()
+    assert float(p[0]) == pytest.approx(0.9)          # partial gradient not applied
