@@ -28,8 +28,78 @@ SHIMS = os.path.join(HERE, "shims")
 REF_DENSE_WARMUP = {"vgg16": 512, "lstman4": 128, "lstm": 128, "bert": 0}
 
 
+SPARSE_PHASE = "sparse (after the workload's hard-coded dense warm-up, as in the reference)"
+
+
 def _unavailable(why: str) -> dict:
     return {"impl": "reference", "unavailable": why}
+
+
+def _canonical(model, dnn, dataset, bs, world, seq, compressor, density, n_params, dense_warm, phase):
+    """Same keys / values as the other arm's ``config`` (bench.canonical_config)."""
+    return {"model": dnn, "dataset_shape": dataset, "global_batch": bs * world, "per_gpu_batch": bs,
+            "seq_len": seq if model == "bert" else None, "parallelism": "dp%d" % world, "compressor": compressor,
+            "density": density, "params": n_params, "dense_warmup_steps_untimed": dense_warm, "timed_phase": phase,
+            "l2": "no explicit flush: params+grads+residual+momentum working set %.0f MB vs 126 MB L2" % (n_params * 20 / 1e6),
+            "math": "fp32 storage and accumulation; torch defaults (cuDNN conv TF32 allowed, fp32 matmul)"}
+
+
+def _write_losses(model: str, size: int, rank: int, losses: dict) -> None:
+    """Leave the arm's training losses (same synthetic stream, same steps as the other arm) in a side file: the other arm
+    reads it for its loss-parity check when it runs on the same box afterwards."""
+    if rank != 0:
+        return
+    import tempfile
+    try:
+        path = os.path.join(tempfile.gettempdir(), "oktopk_bench_refloss_%s_n%d.json" % (model, size))
+        vals = list(losses.values())
+        with open(path, "w") as f:
+            json.dump({"losses": losses, "final": (vals[-1] if vals else None)}, f)
+    except Exception:  # noqa: BLE001
+        pass
+
+
+def run_reference_with_extras(args, MODELS) -> dict:
+    """The flagship reference result plus, when the flagship is VGG-16, the LSTM-AN4 and BERT sub-results.  The three
+    reference programs are separate source trees with same-named modules (``allreducer``, ``compression``, ``settings``
+    ...), so each sub-result runs in a child process per rank (same RANK / WORLD_SIZE, another rendezvous port) under a
+    timeout: a workload the reference cannot finish is reported as such instead of taking the flagship number down."""
+    import subprocess
+    out = run_reference(args, MODELS)
+    if args.model != "vgg16" or getattr(args, "no_extra", False) or os.environ.get("OKTOPK_BENCH_EXTRA", "1") != "1":
+        return out
+    rank = int(os.environ.get("RANK", "0"))
+    extra = {}
+    port0 = int(os.environ.get("MASTER_PORT", "29512"))
+    root = os.path.dirname(HERE)
+    budgets = {"lstman4": float(os.environ.get("OKTOPK_REF_LSTM_TIMEOUT", "420")),
+               "bert": float(os.environ.get("OKTOPK_REF_BERT_TIMEOUT", "300"))}
+    for j, m in enumerate(("lstman4", "bert")):
+        env = dict(os.environ)
+        env["MASTER_PORT"] = str(port0 + 101 + j)
+        env["OKTOPK_BENCH_EXTRA"] = "0"
+        cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--model", m, "--gpus", str(args.gpus),
+               "--steps", str(max(3, min(args.steps, getattr(args, "extra_steps", 10)))), "--warmup", "3", "--no-extra",
+               "--density", str(args.density), "--compressor", args.compressor]
+        try:
+            r = subprocess.run(cmd, env=env, cwd=root, capture_output=True, text=True, timeout=budgets[m])
+            line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            if rank == 0:
+                if line:
+                    sub = json.loads(line[-1])
+                    extra[m] = {k: sub.get(k) for k in ("metric", "value", "unit", "ms_per_step", "steps", "config", "final_loss",
+                                                        "loss", "unavailable", "arm_details") if k in sub}
+                else:
+                    extra[m] = {"unavailable": "no result (rc %d): %s" % (r.returncode, (r.stderr or "")[-300:])}
+        except subprocess.TimeoutExpired:
+            if rank == 0:
+                extra[m] = {"unavailable": "the reference did not finish within %.0f s on this box" % budgets[m]}
+        except Exception as e:  # noqa: BLE001
+            if rank == 0:
+                extra[m] = {"unavailable": repr(e)[:300]}
+    if out is not None:
+        out["extra_models"] = extra
+    return out
 
 
 def run_reference_bert(args, MODELS) -> dict:
@@ -153,6 +223,9 @@ def run_reference_bert(args, MODELS) -> dict:
         step(pool_dev[i % len(pool_dev)])
     sync_all()
 
+    kept = {}
+    marks = sorted({0, args.steps // 2, args.steps - 1})
+
     def timed(fn_batch, read_loss):
         import numpy as np
         if torch.cuda.is_available():
@@ -163,6 +236,8 @@ def run_reference_bert(args, MODELS) -> dict:
             loss = step(fn_batch(i))
             if read_loss:
                 _ = float(loss.detach())
+            elif i in marks:
+                kept[i] = loss.detach().clone()
         if torch.cuda.is_available():
             e1.record()
         sync_all()
@@ -175,7 +250,9 @@ def run_reference_bert(args, MODELS) -> dict:
             ms = float(allv.max())
         return ms, wall
 
-    ms_total, _ = timed(lambda i: pool_dev[i % len(pool_dev)], False)
+    ms_total, _ = timed(lambda i: pool_dev[(args.warmup + i) % len(pool_dev)], False)
+    losses = {"step%d" % (args.warmup + k): float(v) for k, v in sorted(kept.items())}
+    _write_losses(args.model, size, rank, losses)
     h2d = sum(t.numel() * t.element_size() for t in pool_host[0])
     e2e_ms, wall = timed(lambda i: tuple(t.to(dev, non_blocking=True) for t in pool_host[i % len(pool_host)]), True)
     n_params = sum(p.numel() for _n, p in named)
@@ -184,11 +261,10 @@ def run_reference_bert(args, MODELS) -> dict:
         "value": bs * size * args.steps / (ms_total * 1e-3), "unit": "samples/s", "n_gpus": size, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "impl": "reference",
-        "config": {"model": dnn, "dataset_shape": dataset, "global_batch": bs * size, "per_gpu_batch": bs, "seq_len": seq,
-                   "parallelism": "dp%d" % size, "compressor": args.compressor, "density": args.density, "params": n_params,
-                   "layers": layers, "reference_dense_warmup_steps_untimed": 0, "timed_phase": "sparse (the BERT program "
-                   "has no dense warm-up)", "comm": "mpi4py shim over torch.distributed gloo (host NumPy buffers, as in the "
-                   "reference)", "import_only_shims": ["apex", "amp_C", "boto3"]},
+        "config": _canonical(args.model, dnn, dataset, bs, size, seq, args.compressor, args.density, n_params, 0, SPARSE_PHASE),
+        "arm_details": {"layers": layers, "comm": "mpi4py shim over torch.distributed gloo (host NumPy buffers, as in the "
+                        "reference; the image has no MPI)", "import_only_shims": ["apex", "amp_C", "boto3"]},
+        "loss": losses, "final_loss": (list(losses.values())[-1] if losses else None),
         "e2e": {"value": bs * size * args.steps / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": wall / args.steps,
                 "steps": args.steps},
@@ -308,7 +384,7 @@ def run_reference(args, MODELS) -> dict:
             torch.cuda.synchronize()
 
     dense_warm = int(os.environ.get("OKTOPK_REF_DENSE_WARMUP", REF_DENSE_WARMUP[args.model]))
-    phase = "sparse (after the reference's hard-coded %d-iteration dense warm-up)" % dense_warm
+    phase = SPARSE_PHASE
     e2e_steps = args.steps
     if size == 1 and is_sparse:
         # The reference's sparse branches cannot run on one rank: Ok-Topk indexes global_boundaries[0] of a
@@ -328,6 +404,9 @@ def run_reference(args, MODELS) -> dict:
         step(pool_dev[i % len(pool_dev)])
     sync_all()
 
+    kept = {}
+    marks = sorted({0, args.steps // 2, args.steps - 1})
+
     def timed(fn_batch, read_loss, nsteps=None):
         nsteps = args.steps if nsteps is None else nsteps
         if nsteps <= 0:
@@ -340,6 +419,8 @@ def run_reference(args, MODELS) -> dict:
             loss = step(fn_batch(i))
             if read_loss:
                 _ = float(loss.detach())
+            elif i in marks:
+                kept[i] = loss.detach().clone()
         if torch.cuda.is_available():
             e1.record()
         sync_all()
@@ -357,8 +438,11 @@ def run_reference(args, MODELS) -> dict:
             return float(allv.max()), wall
         return float(a[0]), wall
 
-    ms_total, _ = timed(lambda i: pool_dev[i % len(pool_dev)], read_loss=False)
+    base_it = dense_warm + args.warmup
+    ms_total, _ = timed(lambda i: pool_dev[(base_it + i) % len(pool_dev)], read_loss=False)
     value = bs * size * args.steps / (ms_total * 1e-3)
+    losses = {"step%d" % (base_it + k): float(v) for k, v in sorted(kept.items())}
+    _write_losses(args.model, size, rank, losses)
 
     h2d = sum(t.numel() * t.element_size() for t in pool_host[0])
 
@@ -383,10 +467,11 @@ def run_reference(args, MODELS) -> dict:
         "value": value, "unit": "samples/s", "n_gpus": size, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp32", "data": "synthetic", "impl": "reference",
-        "config": {"model": dnn, "dataset_shape": dataset, "global_batch": bs * size, "per_gpu_batch": bs,
-                   "parallelism": "dp%d" % size, "compressor": args.compressor, "density": args.density, "params": n_params,
-                   "reference_dense_warmup_steps_untimed": dense_warm, "timed_phase": phase, "comm": "mpi4py shim over torch.distributed gloo "
-                   "(host NumPy buffers, as in the reference)", "current_density": cur_density},
+        "config": _canonical(args.model, dnn, dataset, bs, size, args.seq_len, args.compressor, args.density, n_params,
+                             dense_warm, phase),
+        "arm_details": {"comm": "mpi4py shim over torch.distributed gloo (host NumPy buffers, as in the reference; the image "
+                        "has no MPI)", "current_density": cur_density},
+        "loss": losses, "final_loss": (list(losses.values())[-1] if losses else None),
         "e2e": e2e, "gpu_launches": 0,
     }
     return out if rank == 0 else None

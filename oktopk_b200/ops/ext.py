@@ -12,8 +12,8 @@ _ERR: Optional[BaseException] = None
 
 # kernels launched by this package since import (the bench reports the delta over its timed region)
 LAUNCH_COUNT = {"total": 0}
-_LAUNCHERS = {"oktopk_run": 1, "gather_run": 1, "dense_run": 1, "kth_abs": 1, "fused_sgd": 1, "fused_bert_adam": 1,
-              "momentum_correct": 1, "clip_by_norm": 2}
+_LAUNCHERS = {"oktopk_run": 1, "gather_run": 1, "gtopk_run": 1, "dense_run": 1, "kth_abs": 1, "fused_sgd": 1,
+              "fused_bert_adam": 1, "momentum_correct": 1, "clip_by_norm": 2, "land_grads": 1}
 
 
 class _CountingModule:
@@ -29,6 +29,8 @@ class _CountingModule:
             n = per_call
             if name == "oktopk_run" and isinstance(a[9], dict) and a[9].get("split_phases"):
                 n = 7
+            if name == "land_grads":
+                n = max(1, (len(a[0]) + 95) // 96)
             LAUNCH_COUNT["total"] += n
             LAUNCH_COUNT[name] = LAUNCH_COUNT.get(name, 0) + n
             return fn(*a, **kw)

@@ -85,6 +85,7 @@ class _BucketedComm:
                 self._hook_handles.append(p.register_post_accumulate_grad_hook(self._make_hook(p)))
         if self._use_streams:
             self._comm_stream = torch.cuda.Stream()
+        allreducer.add_resync_hook(self._resync_replicas)
         # device-resident learning rates (one float per param group): the fused update kernels read lr from
         # memory so that a captured CUDA graph of the whole step stays valid when the schedule moves
         self._lr_dev = None
@@ -95,6 +96,21 @@ class _BucketedComm:
             self._lr_dev = torch.zeros(max(G, 1), dtype=torch.float32, device=dev0)
             self._lr_pin = [torch.zeros(max(G, 1), dtype=torch.float32).pin_memory() for _ in range(8)]
             self._lr_ev = [None] * len(self._lr_pin)
+
+    def _resync_replicas(self) -> None:
+        """After a handled fault: every replica takes rank 0's parameters (and momentum) again."""
+        w = self._allreducer.world
+        if w.size == 1:
+            return
+        for b in self._buckets:
+            if b.flat_param is not None:
+                w.broadcast(b.flat_param, 0)
+            else:
+                for p in b.params:
+                    w.broadcast(p.data, 0)
+            for t in self._flat_state.get(b.index, {}).values():
+                if torch.is_tensor(t):
+                    w.broadcast(t, 0)
 
     def _group_lr(self, gi: int) -> float:
         return float(self.param_groups[gi]["lr"])

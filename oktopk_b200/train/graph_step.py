@@ -11,6 +11,7 @@ the first time it occurs and the host picks the graph from the iteration counter
 """
 from __future__ import annotations
 
+import math
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -30,18 +31,24 @@ class GraphedTrainStep:
         self.enabled = True
         self.pool = None
         self.why_disabled = ""
+        self._precaptured = False
+        self._cap_counters, self._cap_opt_counter = [], None
+        self._loss_of: Dict[Tuple, torch.Tensor] = {}
 
     # ------------------------------------------------------------------ iteration flavour
     def _engines(self):
         return [self.opt._allreducer._engines.get(b.name) for b in self.opt._buckets]
 
-    def _key(self) -> Tuple:
+    def _key(self, counters=None) -> Tuple:
+        """The flavour of the step the engines are about to run (or would run at the given iteration counters)."""
         cfg = self.opt._cfg
         key = [("density", self.opt.get_current_density())]     # k and the guard limits are baked into the launch
-        for eng in self._engines():
+        engines = self._engines()
+        if counters is None:
+            counters = [None if e is None else e.host.counter for e in engines]
+        for eng, c in zip(engines, counters):
             if eng is None:
                 return ("nograph",)
-            c = eng.host.counter
             if (not cfg.sparse) or c < cfg.warmup_iters:
                 key.append(("dense",))
                 continue
@@ -52,11 +59,61 @@ class GraphedTrainStep:
                             it % cfg.repartition_interval == 0))
             elif name == "topkAopt":
                 key.append((it % cfg.topkaopt_recompute_interval == 0,))
-            elif name in ("topkA2", "gtopk"):
-                return ("nograph",)          # host-driven tree / re-selection: not capturable
             else:
                 key.append(("every",))
         return tuple(key)
+
+    def _sparse_flavours(self):
+        """Every (key, representative sparse-iteration index) the schedule can produce -- a handful: for Ok-Topk the
+        common threshold-reuse step, the exact-threshold step (1 in tau) and the exact + re-partition step."""
+        cfg = self.opt._cfg
+        name = self.opt._allreducer.compressor.name
+        if name == "oktopk":
+            period = 1
+            for v in (cfg.local_recompute_interval, cfg.global_recompute_interval, cfg.repartition_interval):
+                period = period * v // math.gcd(period, v)
+        elif name == "topkAopt":
+            period = cfg.topkaopt_recompute_interval
+        else:
+            period = 1
+        seen = {}
+        n_eng = len(self._engines())
+        for it in range(min(period, 1 << 16)):
+            k = self._key([cfg.warmup_iters + it] * n_eng)
+            if k not in seen:
+                seen[k] = it
+        return seen
+
+    def precapture_sparse(self) -> int:
+        """Capture the graph of EVERY sparse-phase flavour now (capturing records launches, it executes nothing), so that
+        the rare exact-threshold / re-partition iterations are replayed like the common one instead of running eagerly
+        inside somebody's timed region.  Engine iteration counters are faked for the capture and restored."""
+        if not self.enabled or self.static_in is None:
+            return 0
+        cfg = self.opt._cfg
+        if not cfg.sparse:
+            return 0
+        engines = self._engines()
+        if any(e is None for e in engines):
+            return 0
+        real = [e.host.counter for e in engines]
+        real_opt = getattr(self.opt, "counter", None)
+        made = 0
+        for key, it in self._sparse_flavours().items():
+            if key in self.graphs or key == ("nograph",):
+                continue
+            for e in engines:
+                e.host.counter = cfg.warmup_iters + it
+            ok = self._capture(key) is not None
+            for e, c in zip(engines, real):
+                e.host.counter = c
+            if real_opt is not None:
+                self.opt.counter = real_opt
+            if not ok:
+                break
+            made += 1
+        self._precaptured = True
+        return made
 
     # ------------------------------------------------------------------ one step
     def _eager(self, batch) -> torch.Tensor:
@@ -73,9 +130,7 @@ class GraphedTrainStep:
             self.eager_left -= 1
             return self._eager(batch)
         key = self._key()
-        if key == ("nograph",) or any(any(f is True for f in k) for k in key[1:]):
-            # rare flavours (exact-threshold / re-partition iterations, 1 in 32..128) stay eager: capturing them
-            # costs more than they save, and the common flavour is what the step time is made of
+        if key == ("nograph",):
             return self._eager(batch)
         if self.static_in is None:
             self.static_in = tuple(t.clone() if torch.is_tensor(t) else t for t in batch)
@@ -86,16 +141,21 @@ class GraphedTrainStep:
                     return self._eager(batch)
                 s.copy_(t, non_blocking=True)
         self.opt.refresh_lr()
+        if not self._precaptured and all(k != ("dense",) for k in key[1:]):
+            self.precapture_sparse()             # first sparse step: capture every flavour of the schedule at once
         g = self.graphs.get(key)
         if g is None:
             g = self._capture(key)
             if g is None:
                 return self._eager(batch)
-        else:
-            for eng in self._engines():
-                eng.host.counter += 1
-            if hasattr(self.opt, "counter"):
-                self.opt.counter += 1
+            for eng, c in zip(self._engines(), self._cap_counters):
+                eng.host.counter = c             # the capture ran the Python side effects; the replay below is the real step
+            if hasattr(self.opt, "counter") and self._cap_opt_counter is not None:
+                self.opt.counter = self._cap_opt_counter
+        for eng in self._engines():
+            eng.host.counter += 1
+        if hasattr(self.opt, "counter"):
+            self.opt.counter += 1
         g.replay()
         ext.LAUNCH_COUNT["total"] += self.launches.get(key, 0)
         self.static_loss = self._loss_of[key]
@@ -105,6 +165,7 @@ class GraphedTrainStep:
         tr = self.tr
         counters = [eng.host.counter for eng in self._engines()]
         opt_counter = getattr(self.opt, "counter", None)
+        self._cap_counters, self._cap_opt_counter = counters, opt_counter
         l0 = ext.LAUNCH_COUNT["total"]
         g = torch.cuda.CUDAGraph()
         try:
@@ -121,7 +182,6 @@ class GraphedTrainStep:
                 # every graph must write the same loss buffer: re-point through a copy node is not possible after
                 # capture, so keep one buffer per graph and expose the latest
                 self.static_loss = out
-            self._loss_of = getattr(self, "_loss_of", {})
             self._loss_of[key] = out
             if self.pool is None:
                 self.pool = g.pool()

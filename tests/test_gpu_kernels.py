@@ -70,7 +70,7 @@ def test_fused_bert_adam_matches_reference_math():
     torch.testing.assert_close(p, pr, rtol=1e-5, atol=1e-6)
 
 
-def _run_engine_vs_oracle(name, n, iters, cfg, tol_count=0):
+def _run_engine_vs_oracle(name, n, iters, cfg, tol_count=0, rtol=0.0):
     from oktopk_b200.parallel.gpu_engine import CudaBucketEngine
     from oktopk_b200.parallel.oracle import run_oracle
     from oktopk_b200.parallel.state import SparseState
@@ -87,9 +87,10 @@ def _run_engine_vs_oracle(name, n, iters, cfg, tol_count=0):
         ref = run_oracle(name, [x.clone()], states, cfg)[0]
         got = eng.grad.cpu()
         st = eng.stats()
-        bad = int((got != ref).sum())
+        ne = (lambda a, b: a != b) if rtol == 0.0 else (lambda a, b: ~torch.isclose(a, b, rtol=rtol, atol=1e-9))
+        bad = int(ne(got, ref).sum())
         assert bad <= tol_count, "%s it %d: %d mismatching elements (stats %s)" % (name, it, bad, st)
-        rbad = int((eng.residual.cpu() != states[0].residual).sum())
+        rbad = int(ne(eng.residual.cpu(), states[0].residual).sum())
         assert rbad <= tol_count, "%s it %d: residual mismatch %d" % (name, it, rbad)
         if tol_count == 0:
             assert st["local_count"] == states[0].last_local_count, (it, st, states[0].last_local_count)
@@ -284,7 +285,9 @@ def test_native_reselect_and_tree_schemes_single_gpu(name):
 def test_norm_clip_on_the_cuda_path(name):
     """VGG/allreducer.py:1372-1379: the incoming gradient is scaled to L2 norm sqrt(1/P)*norm_clip inside the kernel."""
     from oktopk_b200.config import OkTopkConfig
-    _run_engine_vs_oracle(name, 200_000, 3, OkTopkConfig(density=0.01, norm_clip=5.0), tol_count=8)
+    # (the device computes the norm with double accumulation, torch with an fp32 reduction: the scale factor differs in
+    #  the last bit, hence the relative tolerance; the selected SET must still be the oracle's)
+    _run_engine_vs_oracle(name, 200_000, 3, OkTopkConfig(density=0.01, norm_clip=5.0), tol_count=8, rtol=1e-5)
 
 
 def test_land_grads_kernel_copies_every_tensor():
