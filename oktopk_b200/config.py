@@ -36,6 +36,14 @@ class OkTopkConfig:
     overselect_guard_den: int = 3
     overselect_guard_factor: float = 1.03
     overselect_guard_loops: int = 5     # ... at most this many times (0 => no guard, BERT)
+    # Hard over-selection cap (0 = off = the reference's behaviour).  The reference's guard can raise a stale threshold by
+    # at most 1.03^5; its BERT variant has no guard at all and ships 10-80x k entries per rank early in training.  The
+    # fused pack pass tallies a whole geometric ladder of thresholds for free, so when the count is still above
+    # overselect_cap * k after the guard, the threshold keeps climbing coarse rungs (x overselect_cap_factor each) until it
+    # is not: per-rank volume <= overselect_cap * k whatever the staleness.  The skipped entries stay in the residual.
+    overselect_cap: float = 0.0
+    overselect_cap_factor: float = 1.19
+    overselect_cap_rungs: int = 40
     local_adapt_low: float = 2.0 / 3.0  # count < low*k  => thr /= local_adapt_factor
     local_adapt_high: float = 5.0 / 4.0  # count > high*k => thr *= local_adapt_factor
     local_adapt_factor: float = 1.012
@@ -103,6 +111,7 @@ def _vgg() -> OkTopkConfig:
         local_adapt_low=2 / 3, local_adapt_high=5 / 4, local_adapt_factor=1.012,
         global_adapt_low=2 / 3, global_adapt_high=4 / 3, global_adapt_inc=1.008, global_adapt_dec=1.008,
         gaussian_mode="vgg", gaussian_factor=1.02, gaussian_loops=20,
+        overselect_cap=2.0,
     )
 
 
@@ -115,6 +124,7 @@ def _lstm() -> OkTopkConfig:
         local_adapt_low=3 / 4, local_adapt_high=5 / 4, local_adapt_factor=1.012,
         global_adapt_low=3 / 4, global_adapt_high=5 / 4, global_adapt_inc=1.01, global_adapt_dec=1.008,
         gaussian_mode="lstm", gaussian_factor=1.012, gaussian_loops=50,
+        overselect_cap=2.0,
     )
 
 
@@ -128,6 +138,7 @@ def _bert() -> OkTopkConfig:
         global_adapt_low=4 / 5, global_adapt_high=5 / 4, global_adapt_inc=1.036, global_adapt_dec=1.025,
         balanced_allgather=True, sigma_scale=1.0,
         gaussian_mode="bert", gaussian_factor=1.012, gaussian_loops=20,
+        overselect_cap=2.0,
     )
 
 

@@ -321,7 +321,10 @@ static void oktopk_run(uint64_t g, uint64_t res, uint64_t st, const std::vector<
     p.phase_begin = geti("phase_begin", 0);
     p.phase_end = geti("phase_end", PH_END);
     p.guard_loops = geti("guard_loops", 0);
-    if (p.guard_loops > kGuardMax - 1) p.guard_loops = kGuardMax - 1;
+    if (p.guard_loops > kGuardFineMax) p.guard_loops = kGuardFineMax;
+    p.cap_limit = geti("cap_limit", 0);
+    p.cap_rungs = geti("cap_rungs", 40);
+    p.cap_factor = (float)getf("cap_factor", 1.19);
     p.guard_limit = geti("guard_limit", 0);
     p.guard_factor = (float)getf("guard_factor", 1.03);
     p.l_low_cnt = getf("l_low_cnt", 0.0); p.l_high_cnt = getf("l_high_cnt", 1e30);

@@ -177,6 +177,64 @@ static __device__ float grid_kth_abs(const Seg* segs, int nseg, bool remote, uin
 }
 
 // ------------------------------------------------------------------------------------------
+// over-selection ladder (see OktParams): shared-memory thresholds + per-rung tallies
+// ------------------------------------------------------------------------------------------
+struct LadderCfg { int n_fine, n_total; float f_fine, f_coarse; };
+
+__device__ __forceinline__ LadderCfg ladder_cfg(const OktParams& p, bool on) {
+    LadderCfg c;
+    c.n_fine = on ? min(p.guard_loops, kGuardFineMax) : 0;
+    const int coarse = (on && p.cap_limit > 0) ? min(p.cap_rungs, kGuardMax - 1 - c.n_fine) : 0;
+    c.n_total = 1 + c.n_fine + coarse;           // rungs 0 .. n_total-1
+    c.f_fine = p.guard_factor;
+    c.f_coarse = p.cap_factor;
+    return c;
+}
+// thread 0 fills thr[0..n_total) (plain fp32 multiplications: the oracle reproduces them bit for bit), all zero tallies
+__device__ __forceinline__ void ladder_build(float* s_thr, int* s_cnt, const LadderCfg& c, float thr0) {
+    if (threadIdx.x == 0) {
+        float t = thr0;
+        s_thr[0] = t;
+        for (int j = 1; j < c.n_total; ++j) { t *= (j <= c.n_fine) ? c.f_fine : c.f_coarse; s_thr[j] = t; }
+    }
+    for (int j = threadIdx.x; j < kGuardMax; j += blockDim.x) s_cnt[j] = 0;
+    __syncthreads();
+}
+// highest rung j with ax > T_j (ax > T_0 is given)
+__device__ __forceinline__ int ladder_rung(const float* s_thr, int n_total, float ax) {
+    int lo = 0, hi = n_total - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (ax > s_thr[mid]) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+__device__ __forceinline__ void ladder_flush(OktState* st, int* s_cnt) {
+    __syncthreads();
+    if (threadIdx.x < kGuardMax) {
+        const int c = s_cnt[threadIdx.x];
+        if (c) atomicAdd(&st->guard_counts[threadIdx.x], c);
+    }
+    __syncthreads();
+}
+// one thread: choose the rung from the global tallies; returns the threshold, *count = #(|acc| > threshold);
+// zeroes the tallies for the next call
+__device__ __forceinline__ float ladder_pick(OktState* st, const LadderCfg& c, float thr0, int guard_limit, int cap_limit,
+                                             int* count) {
+    int suffix[kGuardMax];
+    int run = 0;
+    for (int j = kGuardMax - 1; j >= 0; --j) { run += __ldcg(&st->guard_counts[j]); suffix[j] = run; }
+    int j = 0;
+    float t = thr0;
+    while (j < c.n_fine && suffix[j] > guard_limit) { ++j; t *= c.f_fine; }
+    if (cap_limit > 0)
+        while (j < c.n_total - 1 && suffix[j] > cap_limit) { ++j; t *= (j <= c.n_fine) ? c.f_fine : c.f_coarse; }
+    *count = suffix[j];
+    for (int q = 0; q < kGuardMax; ++q) st->guard_counts[q] = 0;
+    return t;
+}
+
+// ------------------------------------------------------------------------------------------
 // TMA-fed streaming read: the CTA walks its share of `nvec` float4 (tiles of kTileV float4 dealt round-robin to
 // CTAs) through a STAGES-deep shared-memory ring.  One elected thread arms a stage's mbarrier and issues the
 // cp.async.bulk load STAGES-1 tiles ahead; all threads consume the landed tile from shared memory through

@@ -42,6 +42,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
     __shared__ float s_thr[OKT_MAXP];
     __shared__ int s_misc[OKT_MAXP * 2 + 4];
     __shared__ int s_soff[OKT_MAXP + 1];            // send-slot offsets (entries) per destination, see slot_off()
+    __shared__ float s_lthr[kGuardMax];             // over-selection ladder: thresholds ...
+    __shared__ int s_lcnt[kGuardMax];               // ... and this CTA's per-rung tallies
     __shared__ ChunkSrc s_srcs[OKT_MAXP];
     __shared__ float s_sthr[OKT_MAXP];
     __shared__ Seg s_segs[OKT_MAXP];
@@ -86,24 +88,15 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
         // (1) acc = g + residual -> residual; exact iterations histogram the top digit on the fly,
         //     threshold-reuse iterations count the guard ladder.
         const float thr0 = st->local_thr;
-        float lad[kGuardMax];
-        lad[0] = thr0;
-#pragma unroll
-        for (int j = 1; j < kGuardMax; ++j) lad[j] = lad[j - 1] * p.guard_factor;
-        int gc[kGuardMax];
-#pragma unroll
-        for (int j = 0; j < kGuardMax; ++j) gc[j] = 0;
+        const LadderCfg lcl = ladder_cfg(p, !p.exact_local);
+        ladder_build(s_lthr, s_lcnt, lcl, thr0);
 
         auto visit = [&](float x) {
             if (p.exact_local) {
                 hist_add(s_hist, x, 0, 0u);
             } else {
                 float ax = fabsf(x);
-                if (ax > thr0) {
-                    gc[0]++;
-#pragma unroll
-                    for (int j = 1; j < kGuardMax; ++j) gc[j] += (j <= p.guard_loops && ax > lad[j]) ? 1 : 0;
-                }
+                if (ax > thr0) atomicAdd(&s_lcnt[ladder_rung(s_lthr, lcl.n_total, ax)], 1);
             }
         };
         // Exact iterations: instead of histogramming all n magnitudes (shared-memory atomics on a handful of hot
@@ -188,18 +181,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
             }
             if (blockIdx.x == 0 && tid == 0) { st->local_thr_used = thr; st->cand_cursor = 0; }
         } else {
-#pragma unroll
-            for (int j = 0; j < kGuardMax; ++j) {
-                int c = warp_sum(gc[j]);
-                if (lane == 0 && c) atomicAdd(&st->guard_counts[j], c);
-            }
+            ladder_flush(st, s_lcnt);
             grid_sync(&st->bar);
             if (blockIdx.x == 0 && tid == 0) {
-                float t = thr0;
-                int j = 0;
-                while (j < p.guard_loops && st->guard_counts[j] > p.guard_limit) { t *= p.guard_factor; ++j; }
-                st->local_thr_used = t;
-                for (int q = 0; q < kGuardMax; ++q) st->guard_counts[q] = 0;
+                int cnt;
+                st->local_thr_used = ladder_pick(st, lcl, thr0, p.guard_limit, p.cap_limit, &cnt);
             }
         }
         grid_sync(&st->bar);
@@ -337,14 +323,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
 
         while (true) {
             const bool res_only = two_pass || attempt > 0;              // the accumulator is already in the residual buffer
-            const bool ladder_on = !two_pass;                           // count the guard ladder in this pass
-            float lad[kGuardMax];
-            lad[0] = thr_sel;
-#pragma unroll
-            for (int j = 1; j < kGuardMax; ++j) lad[j] = lad[j - 1] * p.guard_factor;
-            int gc[kGuardMax];
-#pragma unroll
-            for (int j = 0; j < kGuardMax; ++j) gc[j] = 0;
+            const bool ladder_on = !two_pass;                           // count the over-selection ladder in this pass
+            const LadderCfg lc = ladder_cfg(p, ladder_on);
+            ladder_build(s_lthr, s_lcnt, lc, thr_sel);
             dropped = 0;
 
             // one element per lane; every lane of the warp calls this (converged) -- scalar tail only
@@ -356,11 +337,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
                 int d = 0;
                 if (pred) {
                     d = region_of(s_edges, P, i);
-                    gc[0]++;
-                    if (ladder_on) {
-#pragma unroll
-                        for (int j = 1; j < kGuardMax; ++j) gc[j] += (j <= p.guard_loops && ax > lad[j]) ? 1 : 0;
-                    }
+                    atomicAdd(&s_lcnt[lc.n_total > 1 ? ladder_rung(s_lthr, lc.n_total, ax) : 0], 1);
                 }
                 while (todo) {
                     const int leader = __ffs(todo) - 1;
@@ -463,21 +440,18 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
                     }
                 }
                 if (tot == 0) continue;
-                // guard ladder of my selected elements
+                // ladder tallies of my selected elements (shared-memory atomics: only selected elements get here)
+                if (lc.n_total > 1) {
 #pragma unroll
-                for (int u = 0; u < kPackTile; ++u) {
-                    const float xs[4] = {a[u].x, a[u].y, a[u].z, a[u].w};
+                    for (int u = 0; u < kPackTile; ++u) {
+                        const float xs[4] = {a[u].x, a[u].y, a[u].z, a[u].w};
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        if (mybits & (1u << (u * 4 + c))) {
-                            const float ax = fabsf(xs[c]);
-                            gc[0]++;
-                            if (ladder_on) {
-#pragma unroll
-                                for (int j2 = 1; j2 < kGuardMax; ++j2) gc[j2] += (j2 <= p.guard_loops && ax > lad[j2]) ? 1 : 0;
-                            }
-                        }
+                        for (int c = 0; c < 4; ++c)
+                            if (mybits & (1u << (u * 4 + c)))
+                                atomicAdd(&s_lcnt[ladder_rung(s_lthr, lc.n_total, fabsf(xs[c]))], 1);
                     }
+                } else if (lane == 0) {
+                    atomicAdd(&s_lcnt[0], tot);                            // one rung: the warp's count in one go
                 }
                 const int e_first = 4 * (base + (warp << 5));
                 const int e_last = min(n - 1, 4 * (base + (kPackTile - 1) * kThreads + (warp << 5) + 31) + 3);
@@ -553,11 +527,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
                     if (x != 0.f && fabsf(x) == thr_sel) p.res[i] = 0.f;
                 }
             }
-#pragma unroll
-            for (int j = 0; j < kGuardMax; ++j) {
-                int c = warp_sum(gc[j]);
-                if (lane == 0 && c) atomicAdd(&st->guard_counts[j], c);
-            }
+            ladder_flush(st, s_lcnt);
             if (!can_redo) break;
             grid_sync(&st->bar);
             bool over = false;
@@ -583,11 +553,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
         const bool publisher = can_redo ? (blockIdx.x == 0) : last_cta_ticket(&st->tick[0]);
         if (publisher) {
             if (tid == 0) {
-                float t = thr_sel;
-                int j = 0;
-                if (!two_pass)
-                    while (j < p.guard_loops && __ldcg(&st->guard_counts[j]) > p.guard_limit) { t *= p.guard_factor; ++j; }
-                const int cnt = __ldcg(&st->guard_counts[j]);
+                int cnt;
+                const float t = ladder_pick(st, ladder_cfg(p, !two_pass), thr_sel, p.guard_limit, p.cap_limit, &cnt);
                 st->local_thr_used = t;
                 st->pack_thr = thr_sel;
                 st->stat_local_count = cnt;
@@ -595,7 +562,6 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) oktopk_fused_kernel(cons
                 if ((double)cnt < p.l_low_cnt) nt = t / p.l_factor;
                 else if ((double)cnt > p.l_high_cnt) nt = t * p.l_factor;
                 st->local_thr = nt;
-                for (int q = 0; q < kGuardMax; ++q) st->guard_counts[q] = 0;
                 s_thr[0] = t;
                 __threadfence();
             }

@@ -16,7 +16,8 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kChunk = 1024;              // (idx,val) entries per pulled chunk (4 KB + 4 KB)
 constexpr int kHistBins = 2048;           // 11-bit radix digit
 constexpr int kMaxWarpsTotal = 16384;     // per-warp counters for the quantile cuts
-constexpr int kGuardMax = 8;
+constexpr int kGuardMax = 64;            // rungs of the over-selection ladder (fine guard rungs + coarse cap rungs)
+constexpr int kGuardFineMax = 15;         // most fine (reference guard) rungs
 constexpr int kCtasPerSm = 1;           // persistent kernels: one 512-thread CTA per SM (<= 128 registers/thread)
 constexpr int kPackTile = 2;            // 128-bit vectors per thread per tile of the streaming pass
 constexpr int kPackStages = 4;          // TMA ring depth of the streaming pass
@@ -48,7 +49,7 @@ struct OktState {
     int send_cursor[OKT_MAXP];            // per-destination slot cursors (reset in-kernel)
     int gather_cursor;
     int cand_cursor;                      // first-touch candidate list of the reduce phase (reset in-kernel)
-    int guard_counts[kGuardMax];          // #(|acc| > thr0 * f^j)
+    int guard_counts[kGuardMax];          // selected elements whose HIGHEST passed ladder rung is j (suffix sums = #(|acc| > T_j))
     uint32_t sel_prefix;                  // radix-select running prefix / remaining rank
     uint32_t sel_krem;
     int cuts[OKT_MAXP];
@@ -164,8 +165,15 @@ struct OktParams {
     int residual_mode, global_mode;
     int deterministic, pull_tma;
     int phase_begin, phase_end;
+    // Over-selection ladder T_0 = thr, T_j = T_{j-1} * (j <= guard_loops ? guard_factor : cap_factor).  The reference's
+    // guard (VGG/compression.py:392-404) climbs the first guard_loops rungs while the count exceeds guard_limit; the cap
+    // (cap_limit > 0, a B200-side extension: the counts of ALL rungs come out of the same streaming pass for free) keeps
+    // climbing the coarse rungs while the count exceeds cap_limit, so a stale threshold can never ship more than
+    // cap_limit entries per rank.
     int guard_loops, guard_limit;
     float guard_factor;
+    int cap_limit, cap_rungs;
+    float cap_factor;
     double l_low_cnt, l_high_cnt;       // local adaptation bounds, already multiplied by k
     float l_factor;
     double g_low_cnt, g_high_cnt;

@@ -184,6 +184,8 @@ class CudaBucketEngine:
                 guard_loops=cfg.overselect_guard_loops,
                 guard_limit=cfg.overselect_guard_num * k // cfg.overselect_guard_den,
                 guard_factor=cfg.overselect_guard_factor,
+                cap_limit=int(cfg.overselect_cap * k) if cfg.overselect_cap > 0 else 0,
+                cap_rungs=int(cfg.overselect_cap_rungs), cap_factor=float(cfg.overselect_cap_factor),
                 l_low_cnt=cfg.local_adapt_low * k, l_high_cnt=cfg.local_adapt_high * k, l_factor=cfg.local_adapt_factor,
                 g_low_cnt=cfg.global_adapt_low * k, g_high_cnt=cfg.global_adapt_high * k,
                 g_inc=cfg.global_adapt_inc, g_dec=cfg.global_adapt_dec,

@@ -41,16 +41,30 @@ def kth_largest_abs(x: torch.Tensor, k: int) -> float:
 
 
 def guard_threshold(absx: torch.Tensor, thr: float, k: int, cfg: OkTopkConfig) -> float:
-    """``add2residual`` over-selection guard (``VGG/compression.py:392-404``)."""
-    if cfg.overselect_guard_loops <= 0:
+    """``add2residual`` over-selection guard (``VGG/compression.py:392-404``) + the optional hard cap
+    (``OkTopkConfig.overselect_cap``): one geometric ladder ``T_0 = thr, T_j = T_{j-1} * f`` (``f`` = guard factor on the
+    first ``guard_loops`` rungs, cap factor on the coarse rungs after them), climbed while the count is above the guard
+    limit (fine rungs only) and then while it is above the cap.  Mirrors ``ladder_pick`` in ``csrc/devlib.cuh`` with the
+    same fp32 arithmetic."""
+    n_fine = min(max(cfg.overselect_guard_loops, 0), 15)
+    cap_limit = int(cfg.overselect_cap * k) if cfg.overselect_cap > 0 else 0
+    n_coarse = min(cfg.overselect_cap_rungs, 63 - n_fine) if cap_limit > 0 else 0
+    n_total = 1 + n_fine + n_coarse
+    if n_total == 1:
         return thr
     limit = cfg.overselect_guard_num * k // cfg.overselect_guard_den
-    for _ in range(cfg.overselect_guard_loops):
-        if int((absx > thr).sum()) > limit:
-            thr = f32_mul(thr, cfg.overselect_guard_factor)
-        else:
-            break
-    return thr
+
+    def count(t: float) -> int:
+        return int((absx > t).sum())
+    j, t = 0, thr
+    while j < n_fine and count(t) > limit:
+        j += 1
+        t = f32_mul(t, cfg.overselect_guard_factor)
+    if cap_limit > 0:
+        while j < n_total - 1 and count(t) > cap_limit:
+            j += 1
+            t = f32_mul(t, cfg.overselect_guard_factor if j <= n_fine else cfg.overselect_cap_factor)
+    return t
 
 
 def quantile_cuts(sel_idx: torch.Tensor, P: int, n: int) -> List[int]:

@@ -93,9 +93,12 @@ def _exchange_fds(world: World, fd: int, tag: str) -> List[int]:
     sock.settimeout(60.0)
     try:
         world.barrier()                                  # every socket is bound
+        import array
         for r in range(world.size):
             if r != world.rank:
-                socket.send_fds(sock, [struct.pack("i", world.rank)], [fd], 0, name(r))
+                # (socket.send_fds() drops its address argument on CPython <= 3.12: build the SCM_RIGHTS message by hand)
+                sock.sendmsg([struct.pack("i", world.rank)],
+                             [(socket.SOL_SOCKET, socket.SCM_RIGHTS, array.array("i", [fd]))], 0, name(r))
         got = {world.rank: fd}
         while len(got) < world.size:
             msg, fds, _flags, _addr = socket.recv_fds(sock, 16, 1)

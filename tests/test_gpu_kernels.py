@@ -369,3 +369,17 @@ def test_fused_update_is_skipped_when_the_bucket_faulted():
     C.fused_sgd(p.data_ptr(), g.data_ptr(), mom.data_ptr(), n, 0.1, 0.0, 0.0, 0.0, 0, 0, 0, 1.0, _stream(), 0, flag.data_ptr())
     torch.cuda.synchronize()
     assert float(p[0]) == pytest.approx(0.9)          # partial gradient not applied
+
+
+def test_overselect_cap_bounds_the_volume_and_matches_oracle():
+    """overselect_cap=2: even after x10 / x100 gradient-scale jumps a stale threshold never ships more than 2k entries
+    (the ladder keeps climbing), nothing is lost (conservation), and the choice of rung is the oracle's."""
+    from oktopk_b200.config import OkTopkConfig
+    cfg = OkTopkConfig(density=0.01, local_recompute_interval=8, global_recompute_interval=8, repartition_interval=8,
+                       overselect_cap=2.0)
+    hist = _conservation_run("oktopk", 400_003, 12, cfg)
+    assert all(h["local_count"] <= 2 * 4000 for h in hist), [h["local_count"] for h in hist]
+    assert all(h["overflow_send"] == 0 and h["redo"] == 0 for h in hist)
+    cfg2 = OkTopkConfig(density=0.01, local_recompute_interval=6, global_recompute_interval=6, repartition_interval=4,
+                        overselect_cap=1.5, overselect_guard_loops=0)
+    _run_engine_vs_oracle("oktopk", 300_001, 9, cfg2)

@@ -359,7 +359,7 @@ def test_dense_allreduce_nvls_or_peer_path(P):
     if torch.cuda.device_count() < P:
         pytest.skip("needs %d GPUs" % P)
     n = 1_000_003
-    got = run_distributed(_nvls_worker, P, (n,), backend="nccl", timeout=600)
+    got = run_distributed(_nvls_worker, P, (n,), backend="nccl", timeout=240)
     print("NVLS:", got[0][1], got[0][2])
     for it in range(3):
         ref = sum(_grad(it, r, n).double() for r in range(P)) / P
