@@ -78,6 +78,11 @@ def run_reference_with_extras(args, MODELS) -> dict:
         env = dict(os.environ)
         env["MASTER_PORT"] = str(port0 + 101 + j)
         env["OKTOPK_BENCH_EXTRA"] = "0"
+        # torchrun tells its workers to use the AGENT's rendezvous store at MASTER_PORT; the children rendezvous among
+        # themselves on another port, so child rank 0 must host that store itself
+        for k in ("TORCHELASTIC_USE_AGENT_STORE", "TORCHELASTIC_RUN_ID", "TORCHELASTIC_RESTART_COUNT",
+                  "TORCHELASTIC_MAX_RESTARTS", "TORCH_NCCL_ASYNC_ERROR_HANDLING"):
+            env.pop(k, None)
         cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--model", m, "--gpus", str(args.gpus),
                "--steps", str(max(3, min(args.steps, getattr(args, "extra_steps", 10)))), "--warmup", "3", "--no-extra",
                "--density", str(args.density), "--compressor", args.compressor]
@@ -91,9 +96,14 @@ def run_reference_with_extras(args, MODELS) -> dict:
                                                         "loss", "unavailable", "arm_details") if k in sub}
                 else:
                     extra[m] = {"unavailable": "no result (rc %d): %s" % (r.returncode, (r.stderr or "")[-300:])}
-        except subprocess.TimeoutExpired:
+        except subprocess.TimeoutExpired as te:
             if rank == 0:
-                extra[m] = {"unavailable": "the reference did not finish within %.0f s on this box" % budgets[m]}
+                err = te.stderr if te.stderr is not None else b""
+                if isinstance(err, bytes):
+                    err = err.decode("utf-8", "replace")
+                tail = " | ".join(ln.strip() for ln in err.strip().splitlines()[-6:])
+                extra[m] = {"unavailable": "the reference did not finish within %.0f s on this box; stderr tail: %s"
+                                           % (budgets[m], tail[-500:])}
         except Exception as e:  # noqa: BLE001
             if rank == 0:
                 extra[m] = {"unavailable": repr(e)[:300]}

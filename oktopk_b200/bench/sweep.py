@@ -4,7 +4,8 @@
         --sizes 1M,16M,128M,1G --densities 0.1,0.01,0.001 --schemes oktopk,topkSA,gtopk,dense,nccl
 
 For every (n, density, scheme) the bucket is reduced ``--iters`` times on the fused peer-memory kernels
-(``gtopk`` = NCCL p2p + torch ops, ``nccl`` = ``dist.all_reduce``), each call timed with CUDA events on the launching
+(``nccl`` = ``dist.all_reduce``; ``<scheme>_nccl`` = the same sparse scheme on NCCL collectives + torch ops, the strong
+baseline the fused kernels are compared against), each call timed with CUDA events on the launching
 stream and reported as the MAX over ranks of the median.  Reported per row:
 
   * ``ms``            device time of one allreduce call,
@@ -69,13 +70,42 @@ def run(args) -> List[Dict]:
         # a smooth magnitude ramp makes the balanced regions differ from uniform ones
         src.mul_(torch.linspace(0.5, 1.5, steps=1024, device=dev).repeat_interleave((n + 1023) // 1024)[:n])
         for scheme in args.schemes:
-            dens_list = [None] if scheme in ("dense", "nccl") else args.densities
+            dens_list = [None] if scheme in ("dense", "dense_p2p", "dense_nvls", "nccl") else args.densities
+            if scheme.endswith("_nccl") and n > args.nccl_max_n:
+                continue
             for density in dens_list:
                 d = 0.001 if density is None else density
                 k = max(int(n * d), 1)
                 if scheme == "gtopk" and (P & (P - 1)):
                     continue
-                if scheme == "nccl":
+                if scheme.endswith("_nccl"):
+                    # the honest strong baseline: the SAME scheme on NCCL collectives (all_to_all / all_gather handshakes,
+                    # send/recv payloads) + torch ops for selection/scatter (parallel/algorithms.py, backend='dist')
+                    from oktopk_b200.parallel import algorithms
+                    from oktopk_b200.parallel.state import SparseState
+                    base = scheme[:-5]
+                    cfg = okt.OkTopkConfig(density=d, warmup_iters=0, local_recompute_interval=1 << 30,
+                                           global_recompute_interval=1 << 30, repartition_interval=1 << 30, backend="dist")
+                    stt = SparseState(n, P)
+                    buf = src.clone()
+                    times = []
+                    for it in range(args.warmup + args.iters):
+                        buf.copy_(src)
+                        if stt.residual is not None:
+                            stt.residual.zero_()
+                        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        torch.cuda.synchronize()
+                        w.barrier()
+                        a.record()
+                        algorithms.sparse_allreduce(base, buf, stt, cfg, w, d)
+                        b.record()
+                        torch.cuda.synchronize()
+                        if it >= args.warmup:
+                            times.append(a.elapsed_time(b))
+                    moved = 4.0 * stt.last_volume_elems
+                    stats = {"local_count": stt.last_local_count, "global_count": stt.last_global_count}
+                    del buf, stt
+                elif scheme == "nccl":
                     buf = src.clone()
                     times = []
                     for it in range(args.warmup + args.iters):
@@ -97,9 +127,11 @@ def run(args) -> List[Dict]:
                     cfg = okt.OkTopkConfig(density=d, warmup_iters=0, local_recompute_interval=1 << 30,
                                            global_recompute_interval=1 << 30, repartition_interval=1 << 30,
                                            slot_factor=args.slot_factor, gather_factor=args.slot_factor,
-                                           sparse=scheme != "dense", pull_mode=args.pull)
+                                           sparse=not scheme.startswith("dense"), pull_mode=args.pull,
+                                           nvls={"dense_p2p": "off", "dense_nvls": "on"}.get(scheme, "auto"),
+                                           compressor=scheme if not scheme.startswith("dense") else "none")
                     eng = CudaBucketEngine(n, cfg, w, name="sweep")
-                    name = "none" if scheme == "dense" else scheme
+                    name = "none" if scheme.startswith("dense") else scheme
                     times = []
                     for it in range(args.warmup + args.iters):
                         eng.grad.copy_(src)
@@ -134,7 +166,7 @@ def run(args) -> List[Dict]:
                        "ms": ms, "algbw_GBs": 4.0 * n / (ms * 1e-3) / 1e9, "moved_MB": moved / 1e6,
                        "bound_MB": None if density is None else 6 * k * 8.0 * (P - 1) / P / 1e6,
                        "link_GBs": moved / (ms * 1e-3) / 1e9,
-                       "hbm_frac": None if scheme in ("dense", "nccl") else (16.0 * n / (ms * 1e-3) / 1e9) / hbm,
+                       "hbm_frac": None if scheme in ("dense", "dense_p2p", "dense_nvls", "nccl") else (16.0 * n / (ms * 1e-3) / 1e9) / hbm,
                        "local_count": stats.get("local_count"), "global_count": stats.get("global_count"),
                        "overflow": (stats.get("overflow_send", 0) + stats.get("overflow_gather", 0)) if stats else None,
                        "phase_us": {k2: round(v2, 1) for k2, v2 in stats.get("phase_us", {}).items()} if stats else None}
@@ -165,7 +197,9 @@ def main(argv=None) -> int:
     p.add_argument("--schemes", type=lambda s: s.split(","), default=["oktopk", "topkSA", "gtopk", "dense", "nccl"])
     p.add_argument("--iters", type=int, default=10)
     p.add_argument("--warmup", type=int, default=3)
-    p.add_argument("--slot-factor", type=float, default=2.0)
+    p.add_argument("--slot-factor", type=float, default=0.0, help="0 = lossless slot layout (default), > 0 = bounded slots")
+    p.add_argument("--nccl-max-n", type=lambda s: _parse_size(s), default=1 << 28,
+                   help="largest bucket for the *_nccl (torch ops) baselines: torch.topk / nonzero temporaries are several x n")
     p.add_argument("--pull", type=str, default="tma", choices=["tma", "ldg"])
     p.add_argument("--out", type=str, default=None, help="write a markdown table here (rank 0)")
     args = p.parse_args(argv)

@@ -194,6 +194,7 @@ class SymmBlockVMM:
 
 
 _NVLS_STATE = {"decided": None, "why": ""}
+NVLS_MIN_WORLD = 4
 
 
 def nvls_available(world: World) -> bool:
@@ -220,6 +221,8 @@ def make_symm_block(nbytes: int, world: World, nvls: str = "auto"):
     rank together ('on' raises instead)."""
     import os
     mode = os.environ.get("OKTOPK_NVLS", nvls)
+    if mode == "auto" and world.size < NVLS_MIN_WORLD:
+        mode = "off"          # measured (profiles/bench): at P=2 plain peer loads beat the switch-side reduction
     if mode != "off" and world.size > 1 and nvls_available(world):
         blk, err = None, None
         try:

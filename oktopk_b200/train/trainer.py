@@ -81,8 +81,10 @@ class Trainer:
                               and os.environ.get("OKTOPK_CHANNELS_LAST", "1") == "1")
         if self.channels_last:
             self.net = self.net.to(memory_format=torch.channels_last)
-        # (cudnn.benchmark is deliberately left off: its autotune passes empty the caching allocator, which makes the
-        #  next eager step -- the 1-in-32 exact-threshold flavour that is not graph-replayed -- re-cudaMalloc everything)
+        # cuDNN autotuning (opt-in, OKTOPK_CUDNN_BENCHMARK=1): measured 4 % faster device-resident steps on VGG-16 but a
+        # 2.6x slower end-to-end path (profiles/bench/README.md), so it stays off by default.
+        if (cuda_graph and self.channels_last and os.environ.get("OKTOPK_CUDNN_BENCHMARK", "0") == "1"):
+            torch.backends.cudnn.benchmark = True
         if pretrain:
             self.load_checkpoint(pretrain, model_only=True)
         broadcast_parameters(self.net, 0, self.world)

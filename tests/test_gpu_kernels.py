@@ -87,7 +87,7 @@ def _run_engine_vs_oracle(name, n, iters, cfg, tol_count=0, rtol=0.0):
         ref = run_oracle(name, [x.clone()], states, cfg)[0]
         got = eng.grad.cpu()
         st = eng.stats()
-        ne = (lambda a, b: a != b) if rtol == 0.0 else (lambda a, b: ~torch.isclose(a, b, rtol=rtol, atol=1e-9))
+        ne = (lambda a, b: a != b) if rtol == 0.0 else (lambda a, b: ~torch.isclose(a, b, rtol=rtol, atol=2e-8))
         bad = int(ne(got, ref).sum())
         assert bad <= tol_count, "%s it %d: %d mismatching elements (stats %s)" % (name, it, bad, st)
         rbad = int(ne(eng.residual.cpu(), states[0].residual).sum())
