@@ -81,6 +81,11 @@ class OkTopkConfig:
     # the residual) -- 'bounded and conserved'.
     slot_factor: float = 0.0
     gather_factor: float = 0.0
+    # Automatic dense switch: above this density the sparse schemes are predicted (and measured, profiles/bench/sweep_p8.md:
+    # at rho = 0.1 the fused kernel is selection/scatter bound and loses to the NVLS dense kernel) to be slower than a
+    # dense allreduce of the error-compensated gradient, which also is the better gradient -- so the engine adds the
+    # residual into the bucket, clears it and takes the dense kernel.  0 = never switch.
+    dense_switch_density: float = 0.05
     max_redo: int = 12                  # bounded slots: pack passes that may be repeated per call
     redo_factor: float = 1.5            # first threshold raise of the overflow policy (squared on every further attempt)
     land_grads: bool = True             # gradients land in the bucket with ONE multi-tensor copy kernel per bucket (not 1 add/param)

@@ -391,7 +391,6 @@ static void gtopk_run(uint64_t g, uint64_t res, uint64_t st, const std::vector<u
     p.sel_val = P_<float>(o["sel_val"].cast<uint64_t>());
     p.selcap = o["selcap"].cast<int>();
     p.host_fault = o.contains("host_fault") ? P_<int>(o["host_fault"].cast<uint64_t>()) : nullptr;
-    if (k >= (1 << 26)) throw std::runtime_error("gTopk: k too large for the 26-bit mailbox count");
     ck(launch_gtopk(p, grid, S_(stream)), "gtopk launch");
 }
 

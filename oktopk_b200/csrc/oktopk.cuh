@@ -99,7 +99,7 @@ struct SymmLayout {
     size_t cut_mbox;     // uint64 [2][MAXP]
     size_t cut_data;     // int32  [2][MAXP][MAXP]
     size_t done_mbox;    // uint64 [2][MAXP]       "finished reading your memory" flags (dense fallback, tree schemes)
-    size_t tree_mbox;    // uint64 [2][MAXP]       gTopk: per-round list-ready flags ((epoch<<32) | (round<<26) | count)
+    size_t tree_mbox;    // uint64 [2][MAXP]       gTopk: per-round list-ready flags (((epoch<<5)|round) << 32 | count)
     size_t send_idx;     // int32  [scap]          my selections, bucketed by destination region
     size_t send_val;     // float  [scap]
     size_t gat_idx;      // int32  [2][gcap]       my region's globally selected entries

@@ -144,6 +144,17 @@ class CudaBucketEngine:
             if ext_g:
                 g.copy_(self.grad)
             self.last_mode = "dense"
+        elif self._dense_switch(compressor, density):
+            # predicted slower than the dense kernel at this density: reduce the error-compensated gradient densely
+            # (nothing is left behind, so the residual is cleared) -- OkTopkConfig.dense_switch_density
+            if ext_g:
+                self.grad.copy_(g)
+            self.grad.add_(self.residual)
+            self.residual.zero_()
+            self._dense(s)
+            if ext_g:
+                g.copy_(self.grad)
+            self.last_mode = "dense(auto)"
         elif compressor in _FUSED:
             self._fused(compressor, density, s, g if ext_g else self.grad)
         elif compressor in _GATHER:
@@ -156,6 +167,11 @@ class CudaBucketEngine:
             raise KeyError("unknown compressor %r" % (compressor,))
         st.counter += 1
         return g if ext_g else self.grad
+
+    def _dense_switch(self, compressor: str, density: Optional[float]) -> bool:
+        d = self.cfg.density if density is None else density
+        return (self.cfg.dense_switch_density > 0 and d >= self.cfg.dense_switch_density and self.P > 1
+                and compressor in ("oktopk", "topkSA", "topkDSA", "gaussiankSA"))
 
     def _dense(self, s: int) -> None:
         if self.P == 1:

@@ -227,7 +227,7 @@ def test_native_tree_and_reselect_schemes_match_oracle(name, P):
 def test_topkdsa_dense_fallback():
     """Density 0.4: the reduced regions hold >= n/3 non-zeros, the kernel's final phase takes the dense-allgather path
     (reference VGG/allreducer.py:1311-1353) -- same numbers as the oracle, `dense_fallback` reported."""
-    got = _check("topkDSA", 2, 300_000, 3, dict(density=0.4, compressor="topkDSA"))
+    got = _check("topkDSA", 2, 300_000, 3, dict(density=0.4, compressor="topkDSA", dense_switch_density=0.0))
     assert all(got[r][2][it]["dense_fallback"] == 1 for r in range(2) for it in range(3)), got[0][2]
     got = _check("topkDSA", 2, 300_000, 2, dict(density=0.01, compressor="topkDSA"))
     assert all(got[r][2][it]["dense_fallback"] == 0 for r in range(2) for it in range(2))
@@ -367,3 +367,29 @@ def test_dense_allreduce_nvls_or_peer_path(P):
             assert got[r][3] == 0
             torch.testing.assert_close(got[r][0][it].double(), ref, rtol=1e-5, atol=1e-6)
             assert torch.equal(got[r][0][it], got[0][0][it])
+
+
+def test_automatic_dense_switch_at_high_density():
+    """density >= dense_switch_density: the engine reduces the error-compensated gradient with the dense kernel
+    (sum of (g + residual) / P everywhere, residual cleared)."""
+    P, n = 2, 200_000
+    kw = dict(density=0.1, dense_switch_density=0.05)
+    got = run_distributed(_engine_worker, P, ("oktopk", n, 2, kw), backend="nccl", timeout=300)
+    acc = [torch.zeros(n) for _ in range(P)]
+    for it in range(2):
+        ref = sum((_grad(it, r, n) + acc[r]).double() for r in range(P)) / P
+        for r in range(P):
+            torch.testing.assert_close(got[r][0][it].double(), ref, rtol=1e-5, atol=1e-6)
+            assert got[r][2][it]["mode"] == "dense(auto)"
+        acc = [torch.zeros(n) for _ in range(P)]
+    for r in range(P):
+        assert float(got[r][1].abs().max()) == 0.0
+
+
+def test_small_bucket_for_sanitizer_runs():
+    """A deliberately tiny 2-GPU Ok-Topk run (all flavours, both slot layouts): the target of scripts/sanitize.sh's
+    synccheck / racecheck / memcheck passes over the cross-GPU path."""
+    for sf in (0.0, 2.0):
+        _check("oktopk", 2, 65_536, 5, dict(density=0.01, local_recompute_interval=2, global_recompute_interval=2,
+                                           repartition_interval=2, slot_factor=sf, gather_factor=sf))
+    _check("gtopk", 2, 65_536, 2, dict(density=0.01))
