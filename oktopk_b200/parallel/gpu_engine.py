@@ -115,6 +115,7 @@ class CudaBucketEngine:
         self._write_edges(self.host.region_offsets + [self.n])
         self._dist_state: Optional[SparseState] = None
         self.last_mode = ""
+        self._res_clean = False                  # True while the residual is known to be all-zero (dense-switch calls)
 
     # ------------------------------------------------------------------ helpers
     def _stream(self, stream: Optional[torch.cuda.Stream]) -> int:
@@ -149,19 +150,25 @@ class CudaBucketEngine:
             # (nothing is left behind, so the residual is cleared) -- OkTopkConfig.dense_switch_density
             if ext_g:
                 self.grad.copy_(g)
-            self.grad.add_(self.residual)
-            self.residual.zero_()
+            if not self._res_clean:                # a dense call leaves nothing behind: after the first switched call
+                self.grad.add_(self.residual)      # the residual is known to be all-zero and the carry-over is skipped
+                self.residual.zero_()
+                self._res_clean = True
             self._dense(s)
             if ext_g:
                 g.copy_(self.grad)
             self.last_mode = "dense(auto)"
         elif compressor in _FUSED:
+            self._res_clean = False
             self._fused(compressor, density, s, g if ext_g else self.grad)
         elif compressor in _GATHER:
+            self._res_clean = False
             self._gather(compressor, density, s, g if ext_g else self.grad)
         elif compressor in _TREE:
+            self._res_clean = False
             self._tree(compressor, density, s, g if ext_g else self.grad)
         elif compressor in _DIST_ONLY:
+            self._res_clean = False
             self._dist(compressor, density, g if ext_g else self.grad)
         else:
             raise KeyError("unknown compressor %r" % (compressor,))
@@ -333,6 +340,7 @@ class CudaBucketEngine:
         self.host.counter = int(sd["counter"])
         if sd.get("residual") is not None:
             self.residual.copy_(sd["residual"].to(self.device))
+            self._res_clean = False
         if sd["world"] == self.P:
             edges = list(sd["region_offsets"]) + [self.n]
         else:

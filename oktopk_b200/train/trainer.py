@@ -145,17 +145,23 @@ class Trainer:
         if self.is_bert:
             return self.lr                                     # BertAdam schedules internally
         if self.dnn == "lstman4":
-            lr = self.lr / (1.01 ** self.train_epoch)
+            lr = self.lr / (1.01 ** self.train_epoch)           # /1.01 per epoch (:507-512)
         elif self.dnn == "lstm":
-            lr = self.lr * (0.8 ** max(self.train_epoch - 5, 0)) if self.train_epoch > 5 else self.lr
+            # PTB step schedule (:514-529; the first boundary is 23+40 = 63 there, *after* the second one at 60, so the
+            # 0.1x stage never happens: 1x until epoch 63, 0.01x until 80, 0.001x afterwards)
+            ep = self.train_epoch
+            lr = self.lr if ep < 63 else (self.lr * 0.01 if ep < 80 else self.lr * 0.001)
         else:
+            # general schedule (:531-563): linear warm-up over 10 epochs from lr/nworkers, then 0.1x steps at
+            # 81/122/155 (CIFAR-10 and the other small datasets), 30/60/80 (ImageNet), 24/60/80 (PTB models)
             warm = 10
             if e < warm and self.nworkers > 1:
                 lr0 = self.lr / self.nworkers
                 lr = lr0 + (self.lr - lr0) * e / warm
             else:
+                bounds = {"imagenet": (30, 60, 80), "ptb": (24, 60, 80)}.get(self.dataset, (81, 122, 155))
                 lr = self.lr
-                for boundary in (81, 122, 155):
+                for boundary in bounds:
                     if self.train_epoch >= boundary:
                         lr *= 0.1
         for g in self.optimizer.param_groups:
@@ -349,16 +355,49 @@ class Trainer:
         self.iters_per_epoch = max(len(self.loader), 1)
 
     # ------------------------------------------------------------------ checkpoint / resume
-    def save_checkpoint(self, path: str) -> None:
+    def save_checkpoint(self, path: str, collective: bool = True) -> None:
+        """``collective=False`` (signal handlers, per-rank interrupted state): this rank writes one self-contained file,
+        no barrier.  Otherwise collective when world > 1: rank 0 writes the model / optimizer file; EVERY rank writes its own sparse-allreduce
+        state (error-feedback residuals, thresholds, region edges, counters are per-rank quantities: restoring rank 0's
+        residual on all ranks would duplicate its accumulated error and lose everybody else's) next to it as
+        ``<path>.rank<r>``."""
         os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
-        torch.save({"state": self.net.state_dict(), "optimizer": self.optimizer.state_dict(), "epoch": self.train_epoch,
-                    "iter": self.train_iter, "dnn": self.dnn, "cfg": self.cfg.to_dict()}, path)
+        opt_sd = self.optimizer.state_dict()
+        sparse = opt_sd.get("oktopk")
+        if not collective:
+            torch.save({"state": self.net.state_dict(), "optimizer": opt_sd, "epoch": self.train_epoch,
+                        "iter": self.train_iter, "dnn": self.dnn, "cfg": self.cfg.to_dict(), "world": self.nworkers}, path)
+            return
+        if self.nworkers > 1:
+            torch.save({"oktopk": sparse, "rank": self.rank, "world": self.nworkers}, "%s.rank%d" % (path, self.rank))
+        if self.rank == 0:
+            torch.save({"state": self.net.state_dict(), "optimizer": opt_sd, "epoch": self.train_epoch,
+                        "iter": self.train_iter, "dnn": self.dnn, "cfg": self.cfg.to_dict(), "world": self.nworkers}, path)
+        if self.nworkers > 1:
+            self.world.barrier()
+
+    @staticmethod
+    def _load_file(path: str):
+        try:
+            return torch.load(path, map_location="cpu", weights_only=True)     # tensors + plain containers only
+        except Exception:  # noqa: BLE001 - checkpoints written by older versions may hold other picklables
+            return torch.load(path, map_location="cpu", weights_only=False)
 
     def load_checkpoint(self, path: str, model_only: bool = False) -> None:
-        ck = torch.load(path, map_location="cpu", weights_only=False)
+        ck = self._load_file(path)
         self.net.load_state_dict(ck["state"])
         if not model_only:
-            self.optimizer.load_state_dict(ck["optimizer"])
+            opt_sd = dict(ck["optimizer"])
+            mine = "%s.rank%d" % (path, self.rank)
+            if os.path.isfile(mine):
+                per = self._load_file(mine)
+                if per.get("world") == self.nworkers and per.get("oktopk") is not None:
+                    opt_sd["oktopk"] = per["oktopk"]                              # this rank's own residual / thresholds
+            elif self.nworkers > 1 and self.rank != 0 and opt_sd.get("oktopk") is not None:
+                # no per-rank file (single-file checkpoint): do not replicate rank 0's residual on the other ranks
+                opt_sd["oktopk"] = {**opt_sd["oktopk"], "buckets": {
+                    k: {**v, "residual": None} for k, v in opt_sd["oktopk"].get("buckets", {}).items()}}
+            self.optimizer.load_state_dict(opt_sd)
             self.train_epoch, self.train_iter = ck.get("epoch", 0), ck.get("iter", 0)
 
     def close(self) -> None:
@@ -397,7 +436,7 @@ def robust_ssgd(dnn: str, dataset: Optional[str], data_dir: Optional[str], nwork
                                                     "samples_per_s": batch_size * nsteps_update * w.size / dt}, done)
             if max_iters is not None and done >= max_iters:
                 break
-        if checkpoint_dir and w.rank == 0:
+        if checkpoint_dir:                       # collective: every rank saves its own sparse state
             tr.save_checkpoint(os.path.join(checkpoint_dir, "%s-rank0-epoch%d.pth" % (dnn, epoch)))
         if max_iters is not None and done >= max_iters:
             break

@@ -31,7 +31,7 @@ def interrupted_path(directory: str, rank: int = 0) -> str:
 def save_interrupted_state(trainer, directory: str) -> str:
     os.makedirs(directory, exist_ok=True)
     path = interrupted_path(directory, trainer.rank)
-    trainer.save_checkpoint(path)
+    trainer.save_checkpoint(path, collective=False)        # per-rank file, callable from a signal handler
     return path
 
 

@@ -208,3 +208,36 @@ def test_tiny_bucket_gloo_world2_all_schemes():
     out = run_distributed(_tiny_worker, 2, (10,), backend="gloo", timeout=120)
     for name, t in out[0].items():
         assert torch.isfinite(t).all() and torch.equal(t, out[1][name]), name
+
+
+# --------------------------------------------------------------------------------------------- per-rank checkpoints
+def _ckpt_worker(rank, P, directory):
+    import os
+    import oktopk_b200 as okt
+    from oktopk_b200.train.trainer import Trainer
+    cfg = okt.preset("vgg16", density=0.05, warmup_iters=1, local_recompute_interval=2, global_recompute_interval=2)
+    mk = lambda: Trainer(dnn="mnistnet", dataset="mnist", batch_size=4, lr=0.05, compressor="oktopk", density=0.05, cfg=cfg,
+                         device=torch.device("cpu"))
+    tr = mk()
+    for _ in range(4):
+        tr.train_step()
+    path = os.path.join(directory, "mnistnet-rank0-epoch0.pth")
+    tr.save_checkpoint(path)                                   # collective: every rank writes its own sparse state
+    res = [st.residual.clone() for st in tr.optimizer._allreducer._dist_states.values()]
+    tr.close()
+    tr2 = mk()
+    tr2.load_checkpoint(path)
+    res2 = [st.residual.clone() for st in tr2.optimizer._allreducer._dist_states.values()]
+    tr2.close()
+    return res, res2, os.path.isfile("%s.rank%d" % (path, rank))
+
+
+def test_checkpoint_keeps_every_ranks_own_residual(tmp_path):
+    """Error-feedback residuals are per-rank: a resume must give each rank ITS residual back (not rank 0's)."""
+    out = run_distributed(_ckpt_worker, 2, (str(tmp_path),), backend="gloo", timeout=300)
+    for r in range(2):
+        assert out[r][2]
+        assert len(out[r][0]) == len(out[r][1]) >= 1
+        for a, b in zip(out[r][0], out[r][1]):
+            assert torch.equal(a, b)
+    assert any(not torch.equal(a, b) for a, b in zip(out[0][0], out[1][0])), "the two ranks' residuals should differ"
