@@ -129,6 +129,7 @@ def parse_args(argv=None):
     p.add_argument("--trace", type=str, default=None,
                    help="directory: every rank dumps the per-call device trace ring (counts, thresholds, phase times) there")
     p.add_argument("--slot-factor", type=float, default=None, help="bounded slots (default: lossless layout)")
+    p.add_argument("--comm-ctas", type=int, default=None, help="CTAs of the persistent communication kernels (default: 1 per SM)")
     return p.parse_args(argv)
 
 
@@ -204,6 +205,8 @@ def run_model(args, model: str, w, steps: int, warmup: int, with_clocks: bool, d
         over["bucket_elems"] = args.bucket_elems
     if args.slot_factor is not None:
         over["slot_factor"] = over["gather_factor"] = args.slot_factor
+    if args.comm_ctas is not None:
+        over["comm_ctas"] = args.comm_ctas
     cfg = okt.preset(preset, **over)
     tr = Trainer(dnn=dnn, dataset=dataset, batch_size=bs, lr=lr, compressor=args.compressor, density=args.density,
                  compression=args.compressor != "none", cfg=cfg, world=w, seq_len=args.seq_len, backend=args.backend,
@@ -350,7 +353,7 @@ def run_model(args, model: str, w, steps: int, warmup: int, with_clocks: bool, d
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
         "amortised": amort,
         "loss": losses, "final_loss": final, "reference_loss": ref_loss, "loss_check": check,
-        "arm_details": {"buckets": len(stats), "backend": args.backend or "cuda (fused peer-memory kernels)",
+        "arm_details": {"buckets": len(stats), "bucket_elems": cfg.bucket_elems, "comm_ctas": cfg.comm_ctas, "backend": args.backend or "cuda (fused peer-memory kernels)",
                         "channels_last": bool(getattr(tr, "channels_last", False)),
                         "cuda_graph": (None if tr.graphed is None else {"enabled": tr.graphed.enabled,
                                                                          "graphs": len(tr.graphed.graphs),

@@ -84,7 +84,9 @@ class _BucketedComm:
                 self._bucket_of[p] = b
                 self._hook_handles.append(p.register_post_accumulate_grad_hook(self._make_hook(p)))
         if self._use_streams:
-            self._comm_stream = torch.cuda.Stream()
+            # high priority: a bucket's (SM-partitioned) communication kernel should get its SMs as soon as backward
+            # kernels retire CTAs, not after the whole backward queue
+            self._comm_stream = torch.cuda.Stream(priority=-1)
         allreducer.add_resync_hook(self._resync_replicas)
         # device-resident learning rates (one float per param group): the fused update kernels read lr from
         # memory so that a captured CUDA graph of the whole step stays valid when the schedule moves

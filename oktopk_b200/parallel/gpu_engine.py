@@ -84,7 +84,8 @@ class CudaBucketEngine:
             self.gather_grid = min(self.gather_grid, cfg.comm_ctas)
             self.tree_grid = min(self.tree_grid, cfg.comm_ctas)
         # dense two-shot kernel: one CTA per SM, cooperative launch (its per-CTA cross-GPU barrier needs co-residency)
-        self.dense_grid = dense_grid or torch.cuda.get_device_properties(self.device).multi_processor_count
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        self.dense_grid = dense_grid or (min(sms, cfg.comm_ctas) if cfg.comm_ctas > 0 else sms)
         # ---- one symmetric allocation: [grad | comm block | dense flags] -------------------
         self.grad_bytes = _round_up(self.n * 4, 4096)
         self.comm_off = self.grad_bytes
