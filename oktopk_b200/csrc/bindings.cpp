@@ -452,6 +452,27 @@ static void fused_bert_adam(uint64_t p, uint64_t g, uint64_t m, uint64_t v, int 
                               S_(stream)),
        "fused_bert_adam");
 }
+static void bn_forward(uint64_t x, uint64_t y, uint64_t partial, uint64_t gamma, uint64_t beta, uint64_t cbias, uint64_t save_mean,
+                       uint64_t save_invstd, uint64_t rmean, uint64_t rvar, uint64_t nbt, double momentum, double eps, int relu,
+                       int M, int C, uint64_t stream) {
+    if (C % 4 != 0) throw std::runtime_error("bn_forward: channel count must be a multiple of 4");
+    ck(launch_bn_forward(P_<const float>(x), P_<float>(y), P_<float>(partial), P_<const float>(gamma), P_<const float>(beta),
+                         P_<const float>(cbias), P_<float>(save_mean), P_<float>(save_invstd), P_<float>(rmean), P_<float>(rvar),
+                         P_<long long>(nbt), (float)momentum, (float)eps, relu, M, C, S_(stream)), "bn_forward");
+}
+static void bn_backward(uint64_t x, uint64_t dy, uint64_t dx, uint64_t partial, uint64_t gamma, uint64_t beta, uint64_t save_mean,
+                        uint64_t save_invstd, uint64_t dgamma, uint64_t dbeta, int relu, int M, int C, uint64_t stream) {
+    ck(launch_bn_backward(P_<const float>(x), P_<const float>(dy), P_<float>(dx), P_<float>(partial), P_<const float>(gamma),
+                          P_<const float>(beta), P_<const float>(save_mean), P_<const float>(save_invstd), P_<float>(dgamma),
+                          P_<float>(dbeta), relu, M, C, S_(stream)), "bn_backward");
+}
+static void maxpool2_fwd(uint64_t x, uint64_t y, uint64_t arg, int N, int H, int W, int C, uint64_t stream) {
+    if ((C % 4) || (H % 2) || (W % 2)) throw std::runtime_error("maxpool2_fwd: needs C % 4 == 0 and even H, W");
+    ck(launch_maxpool2_fwd(P_<const float>(x), P_<float>(y), P_<unsigned char>(arg), N, H, W, C, S_(stream)), "maxpool2_fwd");
+}
+static void maxpool2_bwd(uint64_t dy, uint64_t arg, uint64_t dx, int N, int H, int W, int C, uint64_t stream) {
+    ck(launch_maxpool2_bwd(P_<const float>(dy), P_<const unsigned char>(arg), P_<float>(dx), N, H, W, C, S_(stream)), "maxpool2_bwd");
+}
 static void momentum_correct(uint64_t g, uint64_t buf, int n, double momentum, uint64_t stream) {
     ck(launch_momentum_correct(P_<float>(g), P_<float>(buf), n, (float)momentum, S_(stream)), "momentum_correct");
 }
@@ -511,6 +532,11 @@ PYBIND11_MODULE(_C, m) {
           py::arg("lr"), py::arg("b1"), py::arg("b2"), py::arg("eps"), py::arg("wd"), py::arg("zero_grad"),
           py::arg("stream"), py::arg("lr_ptr") = 0, py::arg("fault_ptr") = 0);
     m.def("momentum_correct", &momentum_correct);
+    m.def("maxpool2_fwd", &maxpool2_fwd);
+    m.def("maxpool2_bwd", &maxpool2_bwd);
+    m.def("bn_forward", &bn_forward);
+    m.def("bn_backward", &bn_backward);
+    m.def("bn_num_blocks", &bn_num_blocks);
     m.def("clip_by_norm", &clip_by_norm);
     m.attr("MAXP") = OKT_MAXP;
     m.attr("TRACE_LEN") = kTraceLen;

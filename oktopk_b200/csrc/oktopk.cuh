@@ -270,6 +270,17 @@ struct LandParams {
     int count;
 };
 cudaError_t launch_land(const LandParams& lp, float* bucket, cudaStream_t stream);
+// fused (conv-bias +) BatchNorm + ReLU, channels_last fp32, training mode (csrc/bnrelu.cu)
+int bn_num_blocks(int M, int C);
+cudaError_t launch_bn_forward(const float* x, float* y, float* partial, const float* gamma, const float* beta, const float* cbias,
+                              float* save_mean, float* save_invstd, float* rmean, float* rvar, long long* nbt, float momentum,
+                              float eps, int relu, int M, int C, cudaStream_t stream);
+cudaError_t launch_bn_backward(const float* x, const float* dy, float* dx, float* partial, const float* gamma, const float* beta,
+                               const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta, int relu, int M,
+                               int C, cudaStream_t stream);
+cudaError_t launch_maxpool2_fwd(const float* x, float* y, unsigned char* arg, int N, int H, int W, int C, cudaStream_t stream);
+cudaError_t launch_maxpool2_bwd(const float* dy, const unsigned char* arg, float* dx, int N, int H, int W, int C,
+                                cudaStream_t stream);
 cudaError_t launch_momentum_correct(float* g, float* buf, int n, float momentum, cudaStream_t stream);
 cudaError_t launch_l2norm_sq(const float* x, int n, float* out, cudaStream_t stream);
 cudaError_t launch_scale(float* x, int n, const float* norm_sq, float max_norm, cudaStream_t stream);

@@ -175,6 +175,10 @@ __global__ void __launch_bounds__(kLandThreads) land_kernel(const LandParams lp,
     const int numel = lp.numel[t];
     const int begin = part * kLandPerCta;
     const int end = min(numel, begin + kLandPerCta);
+    if (src == nullptr) {                 // parameter without a gradient in this step: its slice of the bucket is zero
+        for (int i = begin + threadIdx.x; i < end; i += kLandThreads) dst[i] = 0.f;
+        return;
+    }
     const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0;
     if (aligned) {
         const int v0 = begin >> 2, v1 = end >> 2;

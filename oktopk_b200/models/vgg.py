@@ -30,9 +30,17 @@ class VGG(nn.Module):
         layers.append(nn.AvgPool2d(kernel_size=1, stride=1))
         self.features = nn.Sequential(*layers)
         self.fc = nn.Linear(512, num_classes)
+        import os
+        self.fuse = os.environ.get("OKTOPK_FUSED_BN", "1") == "1"
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        x = self.features(x)
+        # Conv -> BN -> ReLU runs go through the fused sm_100a batch-norm kernels when the activations are channels_last
+        # fp32 on the GPU in training mode (ops/fused_bn.py); everywhere else this is exactly self.features(x)
+        if self.fuse and x.is_cuda and self.training:
+            from ..ops.fused_bn import run_fused_sequential
+            x = run_fused_sequential(self.features, x)
+        else:
+            x = self.features(x)
         return self.fc(torch.flatten(x, 1))
 
 

@@ -16,7 +16,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent.parent
 CSRC = PKG / "csrc"
 BUILD = CSRC / "build"
-CU_SOURCES = ["oktopk.cu", "gather.cu", "gtopk.cu", "dense.cu", "optim.cu"]
+CU_SOURCES = ["oktopk.cu", "gather.cu", "gtopk.cu", "dense.cu", "optim.cu", "bnrelu.cu"]
 CPP_SOURCES = ["bindings.cpp"]
 HEADERS = ["common.cuh", "oktopk.cuh", "devlib.cuh"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

@@ -169,8 +169,10 @@ class _BucketedComm:
         srcs, offs, numels = [], [], []
         for p, o, v in zip(b.params, b.offsets, b.grad_views):
             g = p.grad
-            if g is None:
-                v.zero_()                         # parameter unused in this step
+            if g is None:                         # no gradient in this step (unused parameter, or a conv bias folded
+                srcs.append(0)                    # into a fused batch-norm): zero-filled by the same launch
+                offs.append(o)
+                numels.append(p.numel())
             elif g.data_ptr() == v.data_ptr():
                 continue                          # already accumulated in place (gradients were never detached)
             elif g.dtype == torch.float32 and g.is_cuda and g.stride() == v.stride():

@@ -383,3 +383,89 @@ def test_overselect_cap_bounds_the_volume_and_matches_oracle():
     cfg2 = OkTopkConfig(density=0.01, local_recompute_interval=6, global_recompute_interval=6, repartition_interval=4,
                         overselect_cap=1.5, overselect_guard_loops=0)
     _run_engine_vs_oracle("oktopk", 300_001, 9, cfg2)
+
+
+@pytest.mark.parametrize("shape", [(16, 64, 32, 32), (16, 128, 16, 16), (16, 512, 2, 2), (4, 96, 5, 7), (2, 1024, 3, 3)])
+@pytest.mark.parametrize("relu", [True, False])
+def test_fused_bias_bn_relu_matches_torch(shape, relu):
+    """csrc/bnrelu.cu against conv-bias add -> nn.BatchNorm2d -> ReLU in plain fp32 torch: output, input gradient,
+    gamma/beta gradients, running statistics; the reference's own bias gradient is rounding noise."""
+    from oktopk_b200.ops.fused_bn import bias_bn_relu
+    torch.manual_seed(sum(shape))
+    N, C, H, W = shape
+    x = (torch.randn(N, C, H, W, device="cuda") * 1.7 + 0.3).contiguous(memory_format=torch.channels_last)
+    cb = torch.randn(C, device="cuda")
+    dy = torch.randn(N, C, H, W, device="cuda").contiguous(memory_format=torch.channels_last)
+    bn_a, bn_b = torch.nn.BatchNorm2d(C).cuda(), torch.nn.BatchNorm2d(C).cuda()
+    with torch.no_grad():
+        bn_a.weight.normal_(1.0, 0.3); bn_a.bias.normal_(0.0, 0.5)
+        bn_b.load_state_dict(bn_a.state_dict())
+    xa = x.clone().requires_grad_(True); xb = x.clone().requires_grad_(True)
+    cba = cb.clone().requires_grad_(True); cbb = cb.clone().requires_grad_(True)
+    for it in range(2):                                     # two steps: running statistics accumulate
+        ya = bias_bn_relu(xa, bn_a, cba, relu)
+        zb = bn_b(xb + cbb.view(1, -1, 1, 1))
+        yb = torch.relu(zb) if relu else zb
+        for t in (xa, xb, cba, cbb, bn_a.weight, bn_a.bias, bn_b.weight, bn_b.bias):
+            t.grad = None
+        ya.backward(dy); yb.backward(dy)
+    assert ya.is_contiguous(memory_format=torch.channels_last)
+    torch.testing.assert_close(ya, yb, rtol=2e-4, atol=2e-5)
+    # an element whose pre-activation is within rounding of zero may take the other side of the ReLU: allow a few
+    bad = int((~torch.isclose(xa.grad, xb.grad, rtol=2e-3, atol=2e-4)).sum())
+    assert bad <= max(4, xa.numel() // 20000), bad
+    torch.testing.assert_close(bn_a.weight.grad, bn_b.weight.grad, rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(bn_a.bias.grad, bn_b.bias.grad, rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(bn_a.running_mean, bn_b.running_mean, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(bn_a.running_var, bn_b.running_var, rtol=1e-4, atol=1e-5)
+    assert int(bn_a.num_batches_tracked) == int(bn_b.num_batches_tracked) == 2
+    assert cba.grad is None                                  # the loss does not depend on a bias in front of a batch-norm ...
+    assert float(cbb.grad.abs().max()) <= 1e-3 * float(dy.abs().sum(dim=(0, 2, 3)).max())     # ... autograd returns noise
+
+
+def test_vgg16_fused_path_trains_like_the_stock_modules():
+    import copy
+    from oktopk_b200.models import create_net
+    torch.manual_seed(0)
+    torch.backends.cudnn.deterministic = True
+    base, _ = create_net(10, "vgg16")
+    base = base.cuda().to(memory_format=torch.channels_last)
+    a, b = copy.deepcopy(base), copy.deepcopy(base)
+    a.fuse, b.fuse = True, False
+    oa = torch.optim.SGD(a.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
+    ob = torch.optim.SGD(b.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
+    x = torch.randn(16, 3, 32, 32, device="cuda").contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 10, (16,), device="cuda")
+    la, lb = [], []
+    for it in range(5):
+        for net, opt, ls in ((a, oa, la), (b, ob, lb)):
+            opt.zero_grad(set_to_none=True)
+            loss = torch.nn.functional.cross_entropy(net(x), y)
+            loss.backward()
+            opt.step()
+            ls.append(float(loss.detach()))
+        if it == 0:                                          # after ONE step the two paths must agree closely everywhere
+            sa, sb = a.state_dict(), b.state_dict()
+            assert list(sa.keys()) == list(sb.keys())
+            for k in sa:
+                if sa[k].dtype.is_floating_point:
+                    torch.testing.assert_close(sa[k], sb[k], rtol=2e-3, atol=2e-4, msg=lambda m, k=k: "%s: %s" % (k, m))
+                else:
+                    assert torch.equal(sa[k], sb[k]), k
+    assert la[0] == pytest.approx(lb[0], rel=1e-4)
+    # (later steps: two fp32 trajectories of a 14.7 M-parameter net drift apart, only the loss level is compared)
+    assert la[-1] == pytest.approx(lb[-1], rel=0.1, abs=0.05), (la, lb)
+
+
+@pytest.mark.parametrize("shape", [(16, 64, 32, 32), (16, 512, 2, 2), (3, 20, 6, 10)])
+def test_maxpool_2x2_channels_last_matches_torch(shape):
+    from oktopk_b200.ops.fused_bn import max_pool_2x2
+    torch.manual_seed(1)
+    pool = torch.nn.MaxPool2d(2, 2)
+    x = torch.relu(torch.randn(*shape, device="cuda")).contiguous(memory_format=torch.channels_last)   # many ties at 0
+    xa = x.clone().requires_grad_(True); xb = x.clone().requires_grad_(True)
+    ya, yb = max_pool_2x2(xa, pool), pool(xb)
+    dy = torch.randn_like(yb)
+    ya.backward(dy); yb.backward(dy)
+    assert torch.equal(ya, yb)
+    assert torch.equal(xa.grad, xb.grad)                     # same arg-max rule for ties (first maximum in window order)
