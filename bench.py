@@ -355,6 +355,7 @@ def run_model(args, model: str, w, steps: int, warmup: int, with_clocks: bool, d
         "loss": losses, "final_loss": final, "reference_loss": ref_loss, "loss_check": check,
         "arm_details": {"buckets": len(stats), "bucket_elems": cfg.bucket_elems, "comm_ctas": cfg.comm_ctas, "backend": args.backend or "cuda (fused peer-memory kernels)",
                         "channels_last": bool(getattr(tr, "channels_last", False)),
+                        "fused_bn_relu_maxpool": bool(getattr(tr.net, "fuse", False)) and bool(getattr(tr, "channels_last", False)),
                         "cuda_graph": (None if tr.graphed is None else {"enabled": tr.graphed.enabled,
                                                                          "graphs": len(tr.graphed.graphs),
                                                                          "why_disabled": tr.graphed.why_disabled})},

@@ -128,6 +128,7 @@ def run(args) -> List[Dict]:
                                            global_recompute_interval=1 << 30, repartition_interval=1 << 30,
                                            slot_factor=args.slot_factor, gather_factor=args.slot_factor,
                                            sparse=not scheme.startswith("dense"), pull_mode=args.pull,
+                                           gselect_mode=args.gselect, dense_switch_density=args.dense_switch,
                                            nvls={"dense_p2p": "off", "dense_nvls": "on"}.get(scheme, "auto"),
                                            compressor=scheme if not scheme.startswith("dense") else "none")
                     eng = CudaBucketEngine(n, cfg, w, name="sweep")
@@ -167,6 +168,7 @@ def run(args) -> List[Dict]:
                        "bound_MB": None if density is None else 6 * k * 8.0 * (P - 1) / P / 1e6,
                        "link_GBs": moved / (ms * 1e-3) / 1e9,
                        "hbm_frac": None if scheme in ("dense", "dense_p2p", "dense_nvls", "nccl") else (16.0 * n / (ms * 1e-3) / 1e9) / hbm,
+                       "mode": stats.get("mode"),
                        "local_count": stats.get("local_count"), "global_count": stats.get("global_count"),
                        "overflow": (stats.get("overflow_send", 0) + stats.get("overflow_gather", 0)) if stats else None,
                        "phase_us": {k2: round(v2, 1) for k2, v2 in stats.get("phase_us", {}).items()} if stats else None}
@@ -200,6 +202,8 @@ def main(argv=None) -> int:
     p.add_argument("--slot-factor", type=float, default=0.0, help="0 = lossless slot layout (default), > 0 = bounded slots")
     p.add_argument("--nccl-max-n", type=lambda s: _parse_size(s), default=1 << 28,
                    help="largest bucket for the *_nccl (torch ops) baselines: torch.topk / nonzero temporaries are several x n")
+    p.add_argument("--gselect", type=str, default="auto", choices=["auto", "list", "scan"])
+    p.add_argument("--dense-switch", type=float, default=0.05, help="automatic dense switch density (0 = off)")
     p.add_argument("--pull", type=str, default="tma", choices=["tma", "ldg"])
     p.add_argument("--out", type=str, default=None, help="write a markdown table here (rank 0)")
     args = p.parse_args(argv)
