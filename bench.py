@@ -302,6 +302,8 @@ def run_model(args, model: str, w, steps: int, warmup: int, with_clocks: bool, d
         tr.flush_losses()
         sync_all()
         h2d0 = tr.prefetch.h2d_bytes
+        for k in tr.host_us:
+            tr.host_us[k] = 0.0
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         f0.record()
@@ -319,6 +321,7 @@ def run_model(args, model: str, w, steps: int, warmup: int, with_clocks: bool, d
                "h2d_bytes_per_step": (tr.prefetch.h2d_bytes - h2d0) // steps, "d2h_bytes_per_step": 4,
                "ms_per_step": float(ms2) / steps, "wall_ms_per_step": wall * 1e3 / steps,
                "losses_read": len(e2e_losses),
+               "host_us_per_step": {k: round(v / max(tr.host_us["steps"], 1), 1) for k, v in tr.host_us.items() if k != "steps"},
                "api": "Trainer.train_step() + Trainer.record_loss(): DataLoader -> pinned staging ring -> H2D -> step; loss D2H per step"}
     stats = tr.optimizer.comm_stats()
     n_params = sum(p.numel() for p in tr.net.parameters())

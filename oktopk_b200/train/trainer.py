@@ -130,6 +130,7 @@ class Trainer:
         self.loss_sum, self.loss_n, self.acc_sum = 0.0, 0, 0.0
         self.hidden = None
         self._loss_pin, self._loss_ev, self._loss_head, self._loss_hist = None, None, 0, []
+        self.host_us = {"next": 0.0, "launch": 0.0, "stage_next": 0.0, "steps": 0}
         self.sparsities: List[float] = []
         self._iter_times: List[float] = []
         # whole-step CUDA graphs (fixed-shape workloads only; AN4 batches vary in length, PTB carries hidden state)
@@ -284,11 +285,18 @@ class Trainer:
     def train_step(self) -> None:
         """One optimizer update = ``nsteps_update`` micro-steps (``VGG/main_trainer.py:83-100``)."""
         if self.graphed is not None and self.graphed.enabled:
+            t0 = time.perf_counter()
             self.net.train()
             self.adjust_learning_rate()
-            self._last_loss = self.graphed.step(self.prefetch.next(defer=True))
+            batch = self.prefetch.next(defer=True)
+            t1 = time.perf_counter()
+            self._last_loss = self.graphed.step(batch)
+            t2 = time.perf_counter()
             self.prefetch.advance()              # host-side staging of the next batch overlaps the replayed step
             self._bookkeep_iter()
+            t3 = time.perf_counter()
+            h = self.host_us                     # host-side cost of a step, by part (observability: is the host the limiter?)
+            h["next"] += (t1 - t0) * 1e6; h["launch"] += (t2 - t1) * 1e6; h["stage_next"] += (t3 - t2) * 1e6; h["steps"] += 1
             return
         self.optimizer.zero_grad()
         for j in range(self.nsteps_update):
@@ -351,6 +359,7 @@ class Trainer:
             self.rank = new_rank
         self.nworkers = nworkers
         self.loader, self.sampler = D.build_loader(self.trainset, self.dataset, self.batch_size, self.rank, nworkers)
+        self.prefetch.close()
         self.prefetch = D.Prefetcher(self.loader, self.device, self.sampler)
         self.iters_per_epoch = max(len(self.loader), 1)
 
@@ -401,6 +410,7 @@ class Trainer:
             self.train_epoch, self.train_iter = ck.get("epoch", 0), ck.get("iter", 0)
 
     def close(self) -> None:
+        self.prefetch.close()
         self.optimizer.close()
         self.writer.close()
 

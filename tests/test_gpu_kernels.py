@@ -469,3 +469,22 @@ def test_maxpool_2x2_channels_last_matches_torch(shape):
     ya.backward(dy); yb.backward(dy)
     assert torch.equal(ya, yb)
     assert torch.equal(xa.grad, xb.grad)                     # same arg-max rule for ties (first maximum in window order)
+
+
+def test_threaded_prefetcher_delivers_the_loader_order_on_the_device():
+    from oktopk_b200.train import data as D
+    ds = D.build_dataset("mnist", None, train=True)
+    loader, sampler = D.build_loader(ds, "mnist", 8, 0, 1, train=False)
+    pf = D.Prefetcher(loader, torch.device("cuda", 0))
+    assert pf.threaded
+    ref = [b for _, b in zip(range(12), iter(loader))]
+    for want in ref:
+        got = pf.next(defer=True)
+        pf.advance()
+        torch.cuda.current_stream().synchronize()
+        assert got[0].is_cuda and torch.equal(got[0].cpu(), want[0]) and torch.equal(got[1].cpu(), want[1])
+    assert pf.h2d_bytes == sum(t.numel() * t.element_size() for b in ref for t in b)
+    pf.close()
+    pf2 = D.Prefetcher(loader, torch.device("cuda", 0), threaded=False)
+    b = pf2.next()
+    assert torch.equal(b[0].cpu(), ref[0][0])
