@@ -55,8 +55,13 @@ class Trainer:
         # The host side of a step is tiny tensor ops (collate 16 images, one pinned copy): on a many-core box an
         # unconstrained intra-op pool costs milliseconds of thread wake-ups per op.  torchrun already pins
         # OMP_NUM_THREADS=1 per rank; do the equivalent for a plain `python` launch.
-        if "OMP_NUM_THREADS" not in os.environ and torch.get_num_threads() > 4:
-            torch.set_num_threads(4)
+        if "OMP_NUM_THREADS" not in os.environ:
+            # GPU training: ONE intra-op thread.  The host ops of a step are tiny (collate 16 images, a 200 KB pinned copy);
+            # split across an OpenMP team they cost team wake-ups / barrier spins, which on a busy or core-limited box took
+            # the staging of one batch from 0.3 ms to 2-2.5 ms (measured: e2e 1.22 vs 2.97 ms/step, profiles/bench/README.md)
+            want = 1 if torch.cuda.is_available() else 4
+            if torch.get_num_threads() > want:
+                torch.set_num_threads(want)
         self.dnn = dnn
         self.dataset = (dataset or _DATASET_OF.get(dnn, "cifar10")).lower()
         self.batch_size, self.lr, self.nsteps_update, self.max_epochs = batch_size, lr, nsteps_update, max_epochs
@@ -236,6 +241,11 @@ class Trainer:
 
     def record_loss(self) -> None:
         """Enqueue the D2H copy of the last step's loss (4 bytes) into a pinned ring slot."""
+        t0 = time.perf_counter()
+        self._record_loss()
+        self.host_us["record_loss"] = self.host_us.get("record_loss", 0.0) + (time.perf_counter() - t0) * 1e6
+
+    def _record_loss(self) -> None:
         if self.device.type != "cuda":
             self._loss_hist.append(float(self._last_loss))
             return
