@@ -28,6 +28,10 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# one OpenMP thread per rank, as torchrun sets for N > 1 (the host side of a step is a handful of tiny tensor ops; an
+# OpenMP team only adds wake-up latency).  Must be in the environment before torch is imported.
+os.environ.setdefault("OMP_NUM_THREADS", "1")
+os.environ.setdefault("MKL_NUM_THREADS", "1")
 
 MODELS = {
     # model: (dnn, dataset, per-GPU batch (reference launch scripts), lr, preset)

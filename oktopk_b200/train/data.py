@@ -383,7 +383,8 @@ class Prefetcher:
         import queue
         try:
             torch.cuda.set_device(self.device)
-            while not self._stop:
+            torch.set_num_threads(1)         # OpenMP's thread count is per calling thread: without this the staging thread
+            while not self._stop:            # splits its 200 KB copies over a full OpenMP team (measured: 0.3 -> 3 ms per batch)
                 item = self._stage()
                 while not self._stop:
                     try:
