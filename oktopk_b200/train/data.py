@@ -302,11 +302,11 @@ def build_loader(dataset: Dataset, name: str, batch_size: int, rank: int, world:
 class Prefetcher:
     """Endless iterator over a DataLoader that stages batches on the device from pinned memory on a side stream.
 
-    On CUDA a background thread runs the host side of the pipeline (DataLoader iteration + collate, copy into a reusable
+    Optionally (``OKTOPK_PREFETCH_THREAD=1`` / ``threaded=True``) a background thread runs the host side of the pipeline (DataLoader iteration + collate, copy into a reusable
     pinned buffer, H2D enqueue on the side stream) up to ``depth`` batches ahead, so the training thread's per-step cost is
     a queue pop and an event wait: with 1.2 ms GPU steps the few hundred microseconds of Python per batch must not sit on
-    the critical path (the reference does a synchronous ``.cuda()`` per step).  ``OKTOPK_PREFETCH_THREAD=0`` keeps
-    everything on the calling thread (``next(defer=True)`` + ``advance()`` then overlap the staging with the step)."""
+    the critical path (the reference does a synchronous ``.cuda()`` per step).  By default everything stays on the
+    calling thread: ``next(defer=True)`` + ``advance()`` overlap the staging of the next batch with the running step."""
 
     def __init__(self, loader: DataLoader, device: torch.device, sampler=None, depth: int = 3, threaded: Optional[bool] = None):
         import os
@@ -321,7 +321,9 @@ class Prefetcher:
         self._nring = depth + 3
         self._ring_events = {}
         if threaded is None:
-            threaded = device.type == "cuda" and os.environ.get("OKTOPK_PREFETCH_THREAD", "1") == "1"
+            # opt-in: measured on shared boxes the extra Python thread buys nothing at 1.2 ms steps (the single-threaded host
+            # path costs ~0.3 ms) and adds GIL / CPU-quota interference (profiles/bench/README.md, "end-to-end host path")
+            threaded = device.type == "cuda" and os.environ.get("OKTOPK_PREFETCH_THREAD", "0") == "1"
         self.threaded = bool(threaded) and self.stream is not None
         self._q = None
         self._stop = False
@@ -374,7 +376,7 @@ class Prefetcher:
                     out.append(host.to(self.device, non_blocking=True))
                 else:
                     out.append(t)
-            done = torch.cuda.Event()
+            done = torch.cuda.Event(blocking=True)       # a host wait on it sleeps instead of spinning a core
             done.record(self.stream)
             self._ring_events[self._ring] = done
         return tuple(out), done, nbytes

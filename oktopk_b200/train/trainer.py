@@ -257,7 +257,7 @@ class Trainer:
             self._loss_ev[i].synchronize()
             self._loss_hist.append(float(self._loss_pin[i]))
         self._loss_pin[i:i + 1].copy_(self._last_loss.detach().reshape(1), non_blocking=True)
-        ev = torch.cuda.Event()
+        ev = torch.cuda.Event(blocking=True)
         ev.record()
         self._loss_ev[i] = ev
         self._loss_head += 1

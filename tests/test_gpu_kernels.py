@@ -477,7 +477,7 @@ def test_threaded_prefetcher_delivers_the_loader_order_on_the_device():
     from oktopk_b200.train import data as D
     ds = D.build_dataset("mnist", None, train=True)
     loader, sampler = D.build_loader(ds, "mnist", 8, 0, 1, train=False)
-    pf = D.Prefetcher(loader, torch.device("cuda", 0))
+    pf = D.Prefetcher(loader, torch.device("cuda", 0), threaded=True)
     assert pf.threaded
     ref = [b for _, b in zip(range(12), iter(loader))]
     for want in ref:
