@@ -255,6 +255,13 @@ def run_model(args, model: str, w, steps: int, warmup: int, with_clocks: bool, d
         step_resident(it)
         it += 1
     sync_all()
+    # Python's cyclic garbage collector must not fire inside a 25 ms timed window: a generation-2 pass over this process'
+    # objects (model, graphs, thousands of tensors) takes tens of milliseconds and lands in whichever call happens to
+    # allocate (measured: e2e 1.21 vs 3.0 ms/step between otherwise identical runs).  Collect now, switch it off for the
+    # timed regions, back on afterwards.  (The library side: GraphedTrainStep freezes the long-lived objects, see there.)
+    import gc
+    gc.collect()
+    gc.disable()
     if sampler is not None:
         sampler.mark()
     launches0 = ext.LAUNCH_COUNT["total"]
@@ -269,6 +276,7 @@ def run_model(args, model: str, w, steps: int, warmup: int, with_clocks: bool, d
             kept[i] = loss.detach().clone()          # 3 tiny device copies; read after the timed region
     e1.record()
     sync_all()
+    gc.enable()
     clocks = sampler.stop() if (sampler is not None and w.rank == 0) else None
     launches = ext.LAUNCH_COUNT["total"] - launches0
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -308,6 +316,8 @@ def run_model(args, model: str, w, steps: int, warmup: int, with_clocks: bool, d
         h2d0 = tr.prefetch.h2d_bytes
         for k in tr.host_us:
             tr.host_us[k] = 0.0
+        gc.collect()
+        gc.disable()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         f0.record()
@@ -317,6 +327,7 @@ def run_model(args, model: str, w, steps: int, warmup: int, with_clocks: bool, d
         e2e_losses = tr.flush_losses()      # waits for every loss copy: all K results are on the host inside the timed region
         f1.record()
         sync_all()
+        gc.enable()
         wall = time.perf_counter() - t0
         ms2 = torch.tensor([max(f0.elapsed_time(f1), 0.0)], device=dev, dtype=torch.float64)
         if w.size > 1:

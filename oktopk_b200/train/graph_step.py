@@ -113,6 +113,12 @@ class GraphedTrainStep:
                 break
             made += 1
         self._precaptured = True
+        # every long-lived object of the training process exists now (model, optimizer state, engines, graphs): move them
+        # to the permanent generation so that the cyclic collector's full passes stop walking them -- a generation-2
+        # collection otherwise stalls a 1.2 ms step loop for tens of milliseconds
+        import gc
+        gc.collect()
+        gc.freeze()
         return made
 
     # ------------------------------------------------------------------ one step
