@@ -39,8 +39,8 @@ __host__ __device__ inline BnGeom bn_geom(int M, int C) {
     g.tpr = g.cv < kBnThreads ? g.cv : kBnThreads;
     g.rpi = kBnThreads / g.tpr;
     if (g.rpi < 1) g.rpi = 1;
-    // ~16 K elements per block: enough blocks to spread a 1 M-element tensor over the GPU, one block for the tiny layers
-    long long want = ((long long)M * C + 16383) / 16384;
+    // ~8 K elements per block: enough blocks to spread a 1 M-element tensor over the GPU, a few blocks for the tiny layers
+    long long want = ((long long)M * C + 8191) / 8192;
     if (want < 1) want = 1;
     if (want > kBnMaxBlocks) want = kBnMaxBlocks;
     int rpb = (int)((M + want - 1) / want);
@@ -53,6 +53,36 @@ __host__ __device__ inline BnGeom bn_geom(int M, int C) {
 
 __device__ __forceinline__ float4 f4_fma(const float4& x, const float4& a, const float4& b) {
     return make_float4(fmaf(x.x, a.x, b.x), fmaf(x.y, a.y, b.y), fmaf(x.z, a.z, b.z), fmaf(x.w, a.w, b.w));
+}
+
+// Combine the per-block partials [nblk][2C] into s_tot[2C] with ALL threads of the block: a tile of up to 256 float4
+// columns at a time, the threads that share a column stride over the blocks, then one shared-memory reduction.  (A loop of
+// "one thread per channel walks all nblk partials" is nblk dependent L2 round trips: 64 x ~0.6 us on the widest layers.)
+__device__ __forceinline__ void bn_combine_partials(const float* __restrict__ partial, int nblk, int C, float* s_tot,
+                                                    float4* s_scr) {
+    const int cols = (2 * C) >> 2;                          // float4 columns of one partial row
+    const float4* p4 = reinterpret_cast<const float4*>(partial);
+    for (int c0 = 0; c0 < cols; c0 += kBnThreads) {
+        const int w = min(kBnThreads, cols - c0);
+        const int groups = kBnThreads / w;
+        const int tx = threadIdx.x % w, ty = threadIdx.x / w;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ty < groups)
+            for (int b = ty; b < nblk; b += groups) {
+                const float4 v = __ldg(p4 + (size_t)b * cols + c0 + tx);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+        s_scr[threadIdx.x] = acc;
+        __syncthreads();
+        if (ty == 0) {
+            for (int j = 1; j < groups; ++j) {
+                const float4 v = s_scr[j * w + tx];
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+            reinterpret_cast<float4*>(s_tot)[c0 + tx] = acc;
+        }
+        __syncthreads();
+    }
 }
 
 // ---------------------------------------------------------------------------------------------- (1) partial statistics
@@ -95,15 +125,14 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const float* __res
                                                                float* __restrict__ rmean, float* __restrict__ rvar,
                                                                long long* __restrict__ nbt, float momentum, float eps, int relu,
                                                                BnGeom g) {
-    extern __shared__ float4 s_ab[];                  // [2][cv]: a = gamma/std, b = beta - mean a
+    extern __shared__ float4 s_ab[];                  // [2][cv]: a = gamma/std, b = beta - mean a; then [2][cv] totals; scratch
+    __shared__ float4 s_scr[kBnThreads];
     const int tx = threadIdx.x % g.tpr, ty = threadIdx.x / g.tpr;
-    // every block combines the partial sums of ALL blocks for its channels, in double (cheap: nblk x C values)
+    float* s_tot = reinterpret_cast<float*>(s_ab) + 2 * g.C;
+    // every block combines the partial sums of ALL blocks (nblk x 2C values, all threads), then mean / 1/std in double
+    bn_combine_partials(partial, g.nblk, g.C, s_tot, s_scr);
     for (int c = threadIdx.x; c < g.C; c += kBnThreads) {
-        double s = 0.0, q = 0.0;
-        for (int b = 0; b < g.nblk; ++b) {
-            s += (double)__ldg(partial + (size_t)b * 2 * g.C + c);
-            q += (double)__ldg(partial + (size_t)b * 2 * g.C + g.C + c);
-        }
+        const double s = (double)s_tot[c], q = (double)s_tot[g.C + c];
         const double mean = s / (double)g.M;
         double var = q / (double)g.M - mean * mean;
         if (var < 0.0) var = 0.0;
@@ -201,14 +230,13 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const float* _
                                                                    const float* __restrict__ save_invstd,
                                                                    const float* __restrict__ partial, float* __restrict__ dgamma,
                                                                    float* __restrict__ dbeta, int relu, BnGeom g) {
-    extern __shared__ float4 s_c[];                   // [2][cv]: dbeta/M, dgamma/M
+    extern __shared__ float4 s_c[];                   // [2][cv]: dbeta/M, dgamma/M; then [2][cv] totals
+    __shared__ float4 s_scr[kBnThreads];
     const int tx = threadIdx.x % g.tpr, ty = threadIdx.x / g.tpr;
+    float* s_tot = reinterpret_cast<float*>(s_c) + 2 * g.C;
+    bn_combine_partials(partial, g.nblk, g.C, s_tot, s_scr);
     for (int c = threadIdx.x; c < g.C; c += kBnThreads) {
-        double sb = 0.0, sg = 0.0;
-        for (int b = 0; b < g.nblk; ++b) {
-            sb += (double)__ldg(partial + (size_t)b * 2 * g.C + c);
-            sg += (double)__ldg(partial + (size_t)b * 2 * g.C + g.C + c);
-        }
+        const double sb = (double)s_tot[c], sg = (double)s_tot[g.C + c];
         reinterpret_cast<float*>(s_c)[c] = (float)(sb / (double)g.M);
         reinterpret_cast<float*>(s_c)[g.C + c] = (float)(sg / (double)g.M);
         if (blockIdx.x == 0) { dbeta[c] = (float)sb; dgamma[c] = (float)sg; }
@@ -253,7 +281,7 @@ cudaError_t launch_bn_forward(const float* x, float* y, float* partial, const fl
                               float* save_mean, float* save_invstd, float* rmean, float* rvar, long long* nbt, float momentum,
                               float eps, int relu, int M, int C, cudaStream_t stream) {
     const BnGeom g = bn_geom(M, C);
-    const size_t sm1 = sizeof(float4) * 2 * g.rpi * g.tpr, sm2 = sizeof(float) * 2 * C;
+    const size_t sm1 = sizeof(float4) * 2 * g.rpi * g.tpr, sm2 = sizeof(float) * 4 * C;
     bn_stats_kernel<<<g.nblk, kBnThreads, sm1, stream>>>(x, partial, g);
     bn_apply_kernel<<<g.nblk, kBnThreads, sm2, stream>>>(x, y, partial, gamma, beta, cbias, save_mean, save_invstd, rmean, rvar,
                                                          nbt, momentum, eps, relu, g);
@@ -264,7 +292,7 @@ cudaError_t launch_bn_backward(const float* x, const float* dy, float* dx, float
                                const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta, int relu, int M,
                                int C, cudaStream_t stream) {
     const BnGeom g = bn_geom(M, C);
-    const size_t sm1 = sizeof(float4) * 2 * g.rpi * g.tpr, sm2 = sizeof(float) * 2 * C;
+    const size_t sm1 = sizeof(float4) * 2 * g.rpi * g.tpr, sm2 = sizeof(float) * 4 * C;
     bn_bwd_reduce_kernel<<<g.nblk, kBnThreads, sm1, stream>>>(x, dy, gamma, beta, save_mean, save_invstd, partial, relu, g);
     bn_bwd_apply_kernel<<<g.nblk, kBnThreads, sm2, stream>>>(x, dy, dx, gamma, beta, save_mean, save_invstd, partial, dgamma,
                                                              dbeta, relu, g);
