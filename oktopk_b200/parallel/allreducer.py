@@ -27,6 +27,10 @@ from .state import SparseState
 from .world import World, world as _world
 
 
+def _capturing() -> bool:
+    return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+
+
 class AllReducer:
     def __init__(self, compression="oktopk", sparse: bool = True, density: float = 0.01, train_epoch: int = 0,
                  cfg: Optional[OkTopkConfig] = None, world: Optional[World] = None, backend: Optional[str] = None,
@@ -108,7 +112,7 @@ class AllReducer:
         thresholds of every call, and every 50 calls the mean per-phase times (``_print_profiling``, :379-443) -- here
         the phases are the device-side stamps of the fused kernel, not host wall-clock.  Synchronous (diagnostic mode)."""
         eng = self._engines[name]
-        if torch.cuda.is_current_stream_capturing():
+        if _capturing():
             return
         st = eng.stats()
         c = self._prof_calls[name] = self._prof_calls.get(name, 0) + 1
@@ -146,7 +150,7 @@ class AllReducer:
         import numpy as np
         from ..compression import gen_threshold_from_normal_distribution
         from ..utils import settings
-        if torch.cuda.is_current_stream_capturing():
+        if _capturing():
             return
         eng = self._engines.get(name)
         st = self._dist_states.get(name)
@@ -271,7 +275,7 @@ class AllReducer:
         ``PeerTimeoutError`` is raised."""
         if not self._engines:
             return
-        if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+        if _capturing():
             return
         for eng in self._engines.values():
             if eng.poll_fault():

@@ -90,3 +90,49 @@ def test_prefetcher_defer_and_advance_cpu():
     b3 = pf.next()                                                # next() stages on demand if advance() was skipped
     for got, want in zip((b0, b1, b2, b3), ref):
         assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+
+
+def test_profiling_flags_on_the_dist_path(tmp_path, monkeypatch, capsys):
+    """settings.PROFILING_GRAD / PROFILING_NORM (VGG/allreducer.py:854-888,1361-1418; VGG/main_trainer.py:107-139):
+    gradient / threshold snapshots at chosen iterations, and the (gtopk_norm, randk_norm, upbound, xnorm, dense_std)
+    tuples saved per epoch."""
+    import numpy as np
+    from oktopk_b200.config import OkTopkConfig
+    from oktopk_b200.parallel.allreducer import AllReducer
+    from oktopk_b200.utils import settings
+    monkeypatch.setattr(settings, "PROFILING_GRAD", True)
+    monkeypatch.setattr(settings, "PROFILING_NORM", True)
+    monkeypatch.setattr(settings, "PREFIX", str(tmp_path))
+    monkeypatch.setenv("OKTOPK_GRAD_DUMP_ITERS", "1-1")
+    ar = AllReducer("topkA", True, 0.05, cfg=OkTopkConfig(density=0.05, compressor="topkA"))
+    for it in range(3):
+        g = torch.randn(2000, generator=torch.Generator().manual_seed(it))
+        ar.run(g)
+    out = capsys.readouterr().out
+    assert "ok_gk_local_thrds" in out
+    assert (tmp_path / "localgrad1_k100.npy").exists() and (tmp_path / "localthrds1_k100.npy").exists()
+    assert len(ar._profiling_norms) == 3 and len(ar.profile_records) == 3
+    gt, rk, ub, xn, sd = ar._profiling_norms[-1]
+    assert 0 <= gt <= xn and rk <= xn + 1e-6 and ub < xn
+    ar.save_profiling_norms(str(tmp_path), 0)
+    arr = np.load(tmp_path / "gtopknorm-rank0-epoch0.npy")
+    assert arr.shape == (3,) and ar._profiling_norms == []
+
+
+def test_lr_schedule_boundaries_follow_the_reference():
+    """ImageNet 30/60/80, PTB-LSTM 1x until epoch 63 then 0.01x / 0.001x (VGG/dl_trainer.py:514-563)."""
+    from oktopk_b200.train.trainer import Trainer
+    tr = Trainer(dnn="mnistnet", dataset="mnist", batch_size=4, lr=1.0, compressor="none", compression=False,
+                 device=torch.device("cpu"))
+    tr.dataset = "imagenet"
+    lrs = {}
+    for ep in (0, 29, 30, 59, 60, 80):
+        tr.train_epoch, tr.train_iter = ep, ep * tr.iters_per_epoch
+        lrs[ep] = tr.adjust_learning_rate()
+    assert lrs[29] == pytest.approx(1.0) and lrs[30] == pytest.approx(0.1) and lrs[60] == pytest.approx(0.01) \
+        and lrs[80] == pytest.approx(0.001)
+    tr.dnn = "lstm"
+    for ep, want in ((10, 1.0), (62, 1.0), (63, 0.01), (79, 0.01), (80, 0.001)):
+        tr.train_epoch = ep
+        assert tr.adjust_learning_rate() == pytest.approx(want), ep
+    tr.close()
