@@ -163,6 +163,7 @@ class GraphedTrainStep:
         if hasattr(self.opt, "counter"):
             self.opt.counter += 1
         g.replay()
+        self.opt._allreducer.poll_faults()       # pinned host mirror of the device fault words: a plain load per bucket
         ext.LAUNCH_COUNT["total"] += self.launches.get(key, 0)
         self.static_loss = self._loss_of[key]
         return self.static_loss
