@@ -435,9 +435,19 @@ def sparse_allreduce(name: str, g: torch.Tensor, st: SparseState, cfg: OkTopkCon
                      density: Optional[float] = None) -> torch.Tensor:
     """Dispatch on the compressor name exactly like ``AllReducer.run`` (``VGG/allreducer.py:573-1622``):
     dense during warm-up / for ``none``, else the named scheme.  Advances the bucket counter."""
+    from .oracle import dense_switch_applies
+    d = cfg.density if density is None else density
     if (not cfg.sparse) or name in ("none", None) or st.counter < cfg.warmup_iters:
         dense_allreduce(g, world)
         st.last_mode = "dense"
+        st.last_volume_elems = 2 * g.numel() * (world.size - 1) // max(world.size, 1)
+    elif dense_switch_applies(name, d, cfg, world.size):
+        with torch.no_grad():                     # same rule as the CUDA engine (gpu_engine._dense_switch)
+            res = st.ensure_residual(g)
+            g.add_(res)
+            res.zero_()
+        dense_allreduce(g, world)
+        st.last_mode = "dense(auto)"
         st.last_volume_elems = 2 * g.numel() * (world.size - 1) // max(world.size, 1)
     else:
         ALGORITHMS[name](g, st, cfg, world, density)

@@ -177,9 +177,9 @@ class CudaBucketEngine:
         return g if ext_g else self.grad
 
     def _dense_switch(self, compressor: str, density: Optional[float]) -> bool:
+        from .oracle import dense_switch_applies
         d = self.cfg.density if density is None else density
-        return (self.cfg.dense_switch_density > 0 and d >= self.cfg.dense_switch_density and self.P > 1
-                and compressor in ("oktopk", "topkSA", "topkDSA", "gaussiankSA"))
+        return dense_switch_applies(compressor, d, self.cfg, self.P)
 
     def _dense(self, s: int) -> None:
         if self.P == 1:

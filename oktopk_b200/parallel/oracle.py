@@ -435,12 +435,28 @@ ORACLES = {
 }
 
 
+def dense_switch_applies(name: str, density: float, cfg: OkTopkConfig, world: int) -> bool:
+    """The rule shared by the oracle, the torch.distributed path and the CUDA engine."""
+    return (cfg.dense_switch_density > 0 and density >= cfg.dense_switch_density and world > 1
+            and name in ("oktopk", "topkSA", "topkDSA", "gaussiankSA"))
+
+
 def run_oracle(name: str, grads, states, cfg: OkTopkConfig, density=None):
     """One reduction of every rank's bucket, warm-up handled, counters advanced."""
+    d = cfg.density if density is None else density
     if (not cfg.sparse) or name in ("none", None) or states[0].counter < cfg.warmup_iters:
         out = dense_oracle(grads)
         for st in states:
             st.last_mode = "dense"
+    elif dense_switch_applies(name, d, cfg, len(grads)):
+        # automatic dense switch (OkTopkConfig.dense_switch_density): the error-compensated gradient is reduced densely,
+        # nothing is left behind
+        for g, st in zip(grads, states):
+            res = st.ensure_residual(g)
+            g.add_(res)
+            res.zero_()
+            st.last_mode = "dense(auto)"
+        out = dense_oracle(grads)
     else:
         out = ORACLES[name](grads, states, cfg, density)
     for st in states:

@@ -99,7 +99,13 @@ def test_gtopk_gloo_world4_tree():
 
 def test_topkdsa_dense_fallback_gloo():
     # density high enough that the reduced regions hold >= n/3 non-zeros => dense Allgatherv branch (VGG:1346-1353)
-    _check("topkSA", 2, n=3000, iters=3, density=0.4)
+    _check("topkSA", 2, n=3000, iters=3, density=0.4, dense_switch_density=0.0)
+
+
+def test_dense_switch_gloo_matches_oracle():
+    """density >= dense_switch_density: the dist path and the oracle both reduce (gradient + residual) densely."""
+    got = _check("oktopk", 2, n=3000, iters=4, density=0.1, dense_switch_density=0.05, exact=False)
+    assert got[0][2][-1] is not None
 
 
 # --------------------------------------------------------------------------------------------- optimizer wrapper
@@ -215,8 +221,8 @@ def _ckpt_worker(rank, P, directory):
     import os
     import oktopk_b200 as okt
     from oktopk_b200.train.trainer import Trainer
-    cfg = okt.preset("vgg16", density=0.05, warmup_iters=1, local_recompute_interval=2, global_recompute_interval=2)
-    mk = lambda: Trainer(dnn="mnistnet", dataset="mnist", batch_size=4, lr=0.05, compressor="oktopk", density=0.05, cfg=cfg,
+    cfg = okt.preset("vgg16", density=0.02, warmup_iters=1, local_recompute_interval=2, global_recompute_interval=2)
+    mk = lambda: Trainer(dnn="mnistnet", dataset="mnist", batch_size=4, lr=0.05, compressor="oktopk", density=0.02, cfg=cfg,
                          device=torch.device("cpu"))
     tr = mk()
     for _ in range(4):

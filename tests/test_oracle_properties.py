@@ -172,7 +172,7 @@ def test_merge_topk_adds_coincident_indices():
 
 def test_warmup_is_dense_and_leaves_sparse_state_untouched():
     P, n = 2, 1000
-    cfg = OkTopkConfig(density=0.05, warmup_iters=3)
+    cfg = OkTopkConfig(density=0.02, warmup_iters=3)
     states = [SparseState(n, P) for _ in range(P)]
     for it in range(3):
         grads = _grads(P, n, it)
