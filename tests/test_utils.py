@@ -136,3 +136,27 @@ def test_lr_schedule_boundaries_follow_the_reference():
         tr.train_epoch = ep
         assert tr.adjust_learning_rate() == pytest.approx(want), ep
     tr.close()
+
+
+def test_graph_step_enumerates_every_flavour_of_the_schedule():
+    """GraphedTrainStep._sparse_flavours: Ok-Topk's schedule has exactly three step flavours (threshold reuse, exact
+    thresholds, exact + re-partition); they are what precapture_sparse() captures up front."""
+    from types import SimpleNamespace
+    from oktopk_b200.config import OkTopkConfig
+    from oktopk_b200.train.graph_step import GraphedTrainStep
+    cfg = OkTopkConfig(density=0.001, warmup_iters=512, local_recompute_interval=32, global_recompute_interval=32,
+                       repartition_interval=64)
+    eng = SimpleNamespace(host=SimpleNamespace(counter=600))
+    opt = SimpleNamespace(_cfg=cfg, _buckets=[SimpleNamespace(name="b0")],
+                          _allreducer=SimpleNamespace(_engines={"b0": eng}, compressor=SimpleNamespace(name="oktopk")),
+                          get_current_density=lambda: 0.001)
+    gs = GraphedTrainStep(SimpleNamespace(optimizer=opt))
+    fl = gs._sparse_flavours()
+    kinds = sorted(k[1] for k in fl)
+    assert kinds == [(False, False, False), (True, True, False), (True, True, True)]
+    assert fl[[k for k in fl if k[1] == (True, True, True)][0]] == 0
+    assert gs._key([512 + 32])[1] == (True, True, False) and gs._key([100])[1] == ("dense",)
+    opt._allreducer.compressor.name = "topkAopt"
+    assert len(gs._sparse_flavours()) == 2
+    opt._allreducer.compressor.name = "gtopk"
+    assert len(gs._sparse_flavours()) == 1               # native tree kernel: one flavour, capturable
