@@ -95,12 +95,21 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const float* __res
     for (int c0 = 0; c0 < g.cv; c0 += g.tpr) {          // column tiles (one tile unless C > 1024)
         const int col = c0 + tx;
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
-        if (ty < g.rpi && col < g.cv)
-            for (int r = row0 + ty; r < row1; r += g.rpi) {
-                const float4 v = __ldg(x4 + (size_t)r * g.cv + col);
+        if (ty < g.rpi && col < g.cv) {
+            auto acc = [&](const float4& v) {
                 s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
                 q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+            };
+            // four independent 128-bit loads in flight per thread (the loop is latency-bound otherwise); same summation order
+            int r = row0 + ty;
+            const size_t st1 = (size_t)g.rpi * g.cv;
+            for (; r + 3 * g.rpi < row1; r += 4 * g.rpi) {
+                const float4* q0 = x4 + (size_t)r * g.cv + col;
+                const float4 v0 = __ldg(q0), v1 = __ldg(q0 + st1), v2 = __ldg(q0 + 2 * st1), v3 = __ldg(q0 + 3 * st1);
+                acc(v0); acc(v1); acc(v2); acc(v3);
             }
+            for (; r < row1; r += g.rpi) acc(__ldg(x4 + (size_t)r * g.cv + col));
+        }
         if (ty < g.rpi) { s_red[ty * g.tpr + tx] = s; s_red[(g.rpi + ty) * g.tpr + tx] = q; }
         __syncthreads();
         if (ty == 0 && col < g.cv) {
@@ -160,11 +169,19 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const float* __res
         const int col = c0 + tx;
         if (ty >= g.rpi || col >= g.cv) continue;
         const float4 a = s_ab[col], b = s_ab[g.cv + col];
-        for (int r = row0 + ty; r < row1; r += g.rpi) {
-            float4 v = f4_fma(__ldg(x4 + (size_t)r * g.cv + col), a, b);
+        auto out = [&](size_t off, const float4& xin) {
+            float4 v = f4_fma(xin, a, b);
             if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-            y4[(size_t)r * g.cv + col] = v;
+            y4[off] = v;
+        };
+        int r = row0 + ty;
+        const size_t st1 = (size_t)g.rpi * g.cv;
+        for (; r + 3 * g.rpi < row1; r += 4 * g.rpi) {
+            const size_t o = (size_t)r * g.cv + col;
+            const float4 v0 = __ldg(x4 + o), v1 = __ldg(x4 + o + st1), v2 = __ldg(x4 + o + 2 * st1), v3 = __ldg(x4 + o + 3 * st1);
+            out(o, v0); out(o + st1, v1); out(o + 2 * st1, v2); out(o + 3 * st1, v3);
         }
+        for (; r < row1; r += g.rpi) { const size_t o = (size_t)r * g.cv + col; out(o, __ldg(x4 + o)); }
     }
 }
 
@@ -191,9 +208,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const float* 
             const float4 a = make_float4(__fmul_rn(gm.x, istd.x), __fmul_rn(gm.y, istd.y), __fmul_rn(gm.z, istd.z), __fmul_rn(gm.w, istd.w));
             const float4 b = make_float4(__fsub_rn(bt.x, __fmul_rn(mean.x, a.x)), __fsub_rn(bt.y, __fmul_rn(mean.y, a.y)),
                                      __fsub_rn(bt.z, __fmul_rn(mean.z, a.z)), __fsub_rn(bt.w, __fmul_rn(mean.w, a.w)));
-            for (int r = row0 + ty; r < row1; r += g.rpi) {
-                const float4 v = __ldg(x4 + (size_t)r * g.cv + col);
-                float4 d = __ldg(d4 + (size_t)r * g.cv + col);
+            auto acc = [&](const float4& v, float4 d) {
                 const float4 xh = make_float4((v.x - mean.x) * istd.x, (v.y - mean.y) * istd.y, (v.z - mean.z) * istd.z,
                                               (v.w - mean.w) * istd.w);
                 if (relu) {       // the forward output was max(0, fma(x, a, b)): same a, b, same fma => the same mask, bit for bit
@@ -204,7 +219,16 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const float* 
                 }
                 sb.x += d.x; sb.y += d.y; sb.z += d.z; sb.w += d.w;
                 sg.x = fmaf(d.x, xh.x, sg.x); sg.y = fmaf(d.y, xh.y, sg.y); sg.z = fmaf(d.z, xh.z, sg.z); sg.w = fmaf(d.w, xh.w, sg.w);
+            };
+            int r = row0 + ty;
+            const size_t st1 = (size_t)g.rpi * g.cv;
+            for (; r + 3 * g.rpi < row1; r += 4 * g.rpi) {         // 8 independent 128-bit loads in flight per thread
+                const size_t o = (size_t)r * g.cv + col;
+                const float4 v0 = __ldg(x4 + o), v1 = __ldg(x4 + o + st1), v2 = __ldg(x4 + o + 2 * st1), v3 = __ldg(x4 + o + 3 * st1);
+                const float4 e0 = __ldg(d4 + o), e1 = __ldg(d4 + o + st1), e2 = __ldg(d4 + o + 2 * st1), e3 = __ldg(d4 + o + 3 * st1);
+                acc(v0, e0); acc(v1, e1); acc(v2, e2); acc(v3, e3);
             }
+            for (; r < row1; r += g.rpi) { const size_t o = (size_t)r * g.cv + col; acc(__ldg(x4 + o), __ldg(d4 + o)); }
         }
         if (ty < g.rpi) { s_red[ty * g.tpr + tx] = sb; s_red[(g.rpi + ty) * g.tpr + tx] = sg; }
         __syncthreads();
@@ -257,9 +281,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const float* _
         const float4 a = make_float4(__fmul_rn(gm.x, istd.x), __fmul_rn(gm.y, istd.y), __fmul_rn(gm.z, istd.z), __fmul_rn(gm.w, istd.w));
         const float4 b = make_float4(__fsub_rn(bt.x, __fmul_rn(mean.x, a.x)), __fsub_rn(bt.y, __fmul_rn(mean.y, a.y)),
                                      __fsub_rn(bt.z, __fmul_rn(mean.z, a.z)), __fsub_rn(bt.w, __fmul_rn(mean.w, a.w)));
-        for (int r = row0 + ty; r < row1; r += g.rpi) {
-            const float4 v = __ldg(x4 + (size_t)r * g.cv + col);
-            float4 d = __ldg(d4 + (size_t)r * g.cv + col);
+        auto out = [&](size_t off, const float4& v, float4 d) {
             const float4 xh = make_float4((v.x - mean.x) * istd.x, (v.y - mean.y) * istd.y, (v.z - mean.z) * istd.z,
                                           (v.w - mean.w) * istd.w);
             if (relu) {
@@ -268,9 +290,18 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const float* _
                 if (!(fmaf(v.z, a.z, b.z) > 0.f)) d.z = 0.f;
                 if (!(fmaf(v.w, a.w, b.w) > 0.f)) d.w = 0.f;
             }
-            o4[(size_t)r * g.cv + col] = make_float4(a.x * (d.x - mb.x - xh.x * mg.x), a.y * (d.y - mb.y - xh.y * mg.y),
-                                                     a.z * (d.z - mb.z - xh.z * mg.z), a.w * (d.w - mb.w - xh.w * mg.w));
+            o4[off] = make_float4(a.x * (d.x - mb.x - xh.x * mg.x), a.y * (d.y - mb.y - xh.y * mg.y),
+                                  a.z * (d.z - mb.z - xh.z * mg.z), a.w * (d.w - mb.w - xh.w * mg.w));
+        };
+        int r = row0 + ty;
+        const size_t st1 = (size_t)g.rpi * g.cv;
+        for (; r + 3 * g.rpi < row1; r += 4 * g.rpi) {
+            const size_t o = (size_t)r * g.cv + col;
+            const float4 v0 = __ldg(x4 + o), v1 = __ldg(x4 + o + st1), v2 = __ldg(x4 + o + 2 * st1), v3 = __ldg(x4 + o + 3 * st1);
+            const float4 e0 = __ldg(d4 + o), e1 = __ldg(d4 + o + st1), e2 = __ldg(d4 + o + 2 * st1), e3 = __ldg(d4 + o + 3 * st1);
+            out(o, v0, e0); out(o + st1, v1, e1); out(o + 2 * st1, v2, e2); out(o + 3 * st1, v3, e3);
         }
+        for (; r < row1; r += g.rpi) { const size_t o = (size_t)r * g.cv + col; out(o, __ldg(x4 + o), __ldg(d4 + o)); }
     }
 }
 
