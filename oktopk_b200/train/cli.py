@@ -49,6 +49,16 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--bucket-elems", type=int, default=None)
     p.add_argument("--backend", type=str, default=None, choices=["auto", "cuda", "dist"])
     p.add_argument("--no-fused", action="store_true", help="phase-per-launch ablation of the persistent kernel")
+    p.add_argument("--slot-factor", type=float, default=None,
+                   help="bounded send/gather slots of slot_factor*k/P entries with the in-kernel overflow policy (default 0: lossless layout)")
+    p.add_argument("--overselect-cap", type=float, default=None,
+                   help="hard bound on the per-rank selection, in units of k (preset: 2; 0 = the reference's behaviour)")
+    p.add_argument("--dense-switch-density", type=float, default=None,
+                   help="densities >= this take the dense kernel (default 0.05; 0 = never)")
+    p.add_argument("--nvls", type=str, default=None, choices=["auto", "on", "off"], help="dense path through the NVSwitch multicast object")
+    p.add_argument("--comm-ctas", type=int, default=None, help="CTAs of the persistent communication kernels (default: one per SM)")
+    p.add_argument("--norm-clip", type=float, default=None, help="TopkA / TopkA2 / gTopk: clip the bucket's L2 norm to sqrt(1/P)*norm_clip")
+    p.add_argument("--trace", type=str, default=None, help="directory: dump the device-side per-call trace ring of every bucket at the end")
     p.add_argument("--deterministic", action="store_true")
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--cuda-graph", action="store_true", help="capture forward+backward+allreduce+update into CUDA graphs")
@@ -94,14 +104,29 @@ def main(argv=None) -> int:
         over["fused"] = False
     if args.deterministic:
         over["deterministic"] = True
+    if args.slot_factor is not None:
+        over["slot_factor"] = over["gather_factor"] = args.slot_factor
+    if args.overselect_cap is not None:
+        over["overselect_cap"] = args.overselect_cap
+    if args.dense_switch_density is not None:
+        over["dense_switch_density"] = args.dense_switch_density
+    if args.nvls is not None:
+        over["nvls"] = args.nvls
+    if args.comm_ctas is not None:
+        over["comm_ctas"] = args.comm_ctas
     cfg = cfg.replace(**over)
     tr = robust_ssgd(dnn, args.dataset, args.data_dir, okt.size(), args.lr, args.batch_size, args.nsteps_update,
                      args.max_epochs, compression=args.compression, compressor=args.compressor,
                      nwpernode=args.nwpernode, sigma_scale=args.sigma_scale, pretrain=args.pretrain,
                      density=args.density, max_iters=args.max_iters, checkpoint_dir=args.checkpoint_dir, cfg=cfg,
                      log_dir=args.log_dir, seq_len=args.max_seq_length, seed=args.seed, backend=args.backend,
-                     cuda_graph=args.cuda_graph, model_kwargs=model_kwargs or None,
+                     cuda_graph=args.cuda_graph, model_kwargs=model_kwargs or None, norm_clip=args.norm_clip,
                      autocast="bf16" if args.bf16 else ("fp16" if args.fp16 else None))
+    if args.trace:
+        import json
+        os.makedirs(args.trace, exist_ok=True)
+        with open(os.path.join(args.trace, "trace_%s_rank%d.json" % (dnn, okt.rank())), "w") as f:
+            json.dump(tr.optimizer._allreducer.trace(), f)
     if okt.rank() == 0:
         print("final loss %.5f after %d iterations" % (tr.last_loss(), tr.train_iter))
     tr.close()

@@ -321,6 +321,20 @@ def test_cli_parser_flag_parity():
     assert b.batch_size == 8 and b.max_iters == 1024 and b.module.endswith("depth=4")
     for c in ("topkA", "topkAopt", "topkA2", "topkSA", "gtopk", "gaussiank", "gaussiankconcat", "gaussiankSA", "none"):
         assert p.parse_args(["--compressor", c]).compressor == c
+    e = p.parse_args("--slot-factor 2 --overselect-cap 1.5 --dense-switch-density 0 --nvls off --comm-ctas 32 --norm-clip 5 "
+                     "--trace /tmp/t".split())
+    assert (e.slot_factor, e.overselect_cap, e.dense_switch_density, e.nvls, e.comm_ctas, e.norm_clip, e.trace) == \
+        (2.0, 1.5, 0.0, "off", 32, 5.0, "/tmp/t")
+
+
+def test_cli_end_to_end_on_cpu_with_engine_flags(tmp_path):
+    """The CLI main() with the round-2 engine flags on the CPU/dist backend (one process)."""
+    from oktopk_b200.train.cli import main
+    rc = main(["--dnn", "mnistnet", "--dataset", "mnist", "--batch-size", "4", "--lr", "0.05", "--compression", "--compressor",
+               "topkA", "--density", "0.02", "--max-iters", "3", "--norm-clip", "5", "--overselect-cap", "0", "--slot-factor", "2",
+               "--dense-switch-density", "0", "--trace", str(tmp_path)])
+    assert rc == 0
+    assert any(f.startswith("trace_mnistnet_rank0") for f in os.listdir(tmp_path))
 
 
 def test_robust_ssgd_driver_runs(tmp_path):
