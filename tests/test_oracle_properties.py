@@ -211,3 +211,30 @@ def test_tiny_buckets_are_handled_by_every_scheme(n, P):
             out = run_oracle(name, g, st, cfg)
             assert all(torch.isfinite(o).all() for o in out), (name, n, P)
             assert all(torch.equal(o, out[0]) for o in out)
+
+
+@pytest.mark.parametrize("P", [1, 4])
+def test_overselect_cap_bounds_the_volume_and_conserves_mass(P):
+    """overselect_cap = 2: after x10 / x100 gradient-scale jumps the stale threshold climbs the coarse ladder rungs until
+    at most 2k entries per rank are selected; nothing is lost (sum acc == sum residual + P * result)."""
+    n, iters = 20_000, 12
+    cfg = OkTopkConfig(density=0.01, local_recompute_interval=8, global_recompute_interval=8, repartition_interval=8,
+                       overselect_cap=2.0)
+    ref = cfg.replace(overselect_cap=0.0)
+    k = int(n * cfg.density)
+    states = [SparseState(n, P) for _ in range(P)]
+    states0 = [SparseState(n, P) for _ in range(P)]
+    worst_uncapped = 0
+    for it in range(iters):
+        scale = 1.0 if it < 3 else (10.0 if it < 6 else 100.0)
+        grads = _grads(P, n, it, scale)
+        acc = sum((g + (st.residual if st.residual is not None else 0)).double() for g, st in zip(grads, states))
+        out = run_oracle("oktopk", [g.clone() for g in grads], states, cfg)
+        run_oracle("oktopk", [g.clone() for g in grads], states0, ref)
+        worst_uncapped = max(worst_uncapped, max(st.last_local_count for st in states0))
+        if it % 8 != 0:                                   # threshold-reuse iterations
+            assert all(st.last_local_count <= 2 * k for st in states), (it, [st.last_local_count for st in states])
+        tot_res = sum(st.residual.double() for st in states)
+        err = (acc - tot_res - P * out[0].double()).abs().max().item()
+        assert err <= 1e-5 * max(acc.abs().max().item(), 1.0), (it, err)
+    assert worst_uncapped > 10 * k                        # without the cap the same stream over-selects massively
